@@ -1,0 +1,536 @@
+// flk_api.cu — C-ABI layer of libflk.so (include/flk.h): handle, device memory, stream, CUDA graph, timing.
+// There is no CPU fallback anywhere in this file: a missing device or a failed launch is an error code.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/flk.h"
+#include "flk_internal.cuh"
+
+namespace flk {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+static float f32_ceil_div(float a, float b) { return std::ceil(a / b); }  // f32 divide, like the reference
+
+int field_alloc(flk_field *f) {
+    const uint64_t cap = f->cap;
+    const uint64_t m = (uint64_t)f->ncell + 1;
+    Store &s = f->s;
+    CUDA_TRY(cudaMalloc(&s.rec, cap * sizeof(Rec)));
+    CUDA_TRY(cudaMalloc(&s.ids, cap * 4));
+    CUDA_TRY(cudaMalloc(&s.cell_start, m * 4));
+    CUDA_TRY(cudaMalloc(&s.trec, cap * sizeof(Rec)));
+    CUDA_TRY(cudaMalloc(&s.tid, cap * 4));
+    CUDA_TRY(cudaMalloc(&s.tkey, cap * 4));
+    CUDA_TRY(cudaMalloc(&s.tslot, cap * 4));
+    CUDA_TRY(cudaMalloc(&s.cnt, m * 4));
+    // one scratch block: (sid, ssrc, skey) during lazy_update; upload / snapshot staging otherwise
+    CUDA_TRY(cudaMalloc(&f->scratch, cap * 20 + 64));
+    s.sid = reinterpret_cast<uint32_t *>(f->scratch);
+    s.ssrc = s.sid + cap;
+    s.skey = s.ssrc + cap;
+    const uint64_t nblk = (m + 2047) / 2048 + 1;
+    CUDA_TRY(cudaMalloc(&s.blocksum, nblk * 4));
+    CUDA_TRY(cudaMalloc(&s.step_dev, 8));
+    CUDA_TRY(cudaMalloc(&s.n_read_dev, 4));
+    CUDA_TRY(cudaMemsetAsync(s.cell_start, 0, m * 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(s.cnt, 0, m * 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(s.step_dev, 0, 8, f->stream));
+    CUDA_TRY(cudaMemsetAsync(s.n_read_dev, 0, 4, f->stream));
+    return FLK_OK;
+}
+
+void field_free(flk_field *f) {
+    Store &s = f->s;
+    cudaFree(s.rec); cudaFree(s.ids); cudaFree(s.cell_start); cudaFree(s.trec); cudaFree(s.tid);
+    cudaFree(s.tkey); cudaFree(s.tslot); cudaFree(s.cnt); cudaFree(f->scratch); cudaFree(s.blocksum);
+    cudaFree(s.step_dev); cudaFree(s.n_read_dev);
+    if (f->d_injected) cudaFree(f->d_injected);
+    if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
+    for (auto &e : f->prof_events) cudaEventDestroy(e);
+    if (f->ev0) cudaEventDestroy(f->ev0);
+    if (f->ev1) cudaEventDestroy(f->ev1);
+    if (f->stream) cudaStreamDestroy(f->stream);
+}
+
+int setup_geometry(flk_field *f, float w, float h, float d, int toroidal) {
+    if (!(w > 0.0f) || !(h > 0.0f) || !(d > 0.0f)) return fail(FLK_E_INVALID, "width, height, discretization must be > 0");
+    Geom &g = f->g;
+    g.W = w; g.H = h; g.d = d; g.toroidal = toroidal ? 1 : 0;
+    const float cw = f32_ceil_div(w, d), ch = f32_ceil_div(h, d);
+    if (cw > 46000.0f || ch > 46000.0f) return fail(FLK_E_UNSUPPORTED, "grid too large (%g x %g cells)", cw, ch);
+    g.mx = (int)cw; g.my = (int)ch;
+    g.dh = g.my + 1;
+    g.ncols = g.mx + 1;
+    g.mode = 0; g.col0 = 0; g.nown = g.mx; g.has_slack = 1;
+    return FLK_OK;
+}
+
+int update_window(flk_field *f) {
+    const float q = std::floor(f->p.radius / f->g.d);
+    int k = (q != q) ? 0 : (int)q;
+    if (k < 0) k = 0;
+    if (f->p.radius > 0.0f && (2 * k + 1 > f->g.mx || 2 * k + 1 > f->g.my) && f->g.toroidal)
+        return fail(FLK_E_UNSUPPORTED, "query window (%d cells) wider than the grid (%d x %d): duplicate visits are not implemented",
+                    2 * k + 1, f->g.mx, f->g.my);
+    if (f->g.mode == 1 && k > 1) return fail(FLK_E_UNSUPPORTED, "strip decomposition implements a one-column halo (k<=1), got k=%d", k);
+    f->p.k = k;
+    return FLK_OK;
+}
+
+// flush host-side single set_object_location calls into the WRITE buffer
+int flush_pending(flk_field *f) {
+    if (f->pend_id.empty()) return FLK_OK;
+    std::vector<uint32_t> id;
+    std::vector<float> loc, ld;
+    id.swap(f->pend_id); loc.swap(f->pend_loc); ld.swap(f->pend_ld);
+    if (f->g.mode == 1) return dist_set_objects(f, id.size(), id.data(), loc.data(), ld.data());
+    return write_append(f, id.size(), id.data(), loc.data(), ld.data());
+}
+
+int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld) {
+    if (n == 0) return FLK_OK;
+    if (f->w_count + n > f->cap)
+        return fail(FLK_E_CAPACITY, "WRITE buffer would hold %llu objects, capacity is %llu",
+                    (unsigned long long)(f->w_count + n), (unsigned long long)f->cap);
+    // staging inside the scratch block (free outside lazy_update; stream order protects it)
+    uint32_t *d_id = reinterpret_cast<uint32_t *>(f->scratch);
+    float2 *d_loc = reinterpret_cast<float2 *>(f->scratch + n * 4 + ((n * 4) % 8));
+    float2 *d_ld = d_loc + n;
+    CUDA_TRY(cudaMemcpyAsync(d_id, id, n * 4, cudaMemcpyHostToDevice, f->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_loc, loc, n * 8, cudaMemcpyHostToDevice, f->stream));
+    CUDA_TRY(cudaMemcpyAsync(d_ld, ld, n * 8, cudaMemcpyHostToDevice, f->stream));
+    launch_ingest(f->g, f->s, (uint32_t)n, d_id, d_loc, d_ld, (uint32_t)f->w_count, f->stream);
+    f->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    f->w_count += n;
+    f->graph_valid = false;
+    return FLK_OK;
+}
+
+int enqueue_lazy_update(flk_field *f, int bump_step) {
+    const uint32_t m = f->ncell + 1;
+    launch_scan(f->s, m, f->stream);
+    launch_scatter(f->s, (uint32_t)f->w_count, f->stream);
+    launch_rank(f->s, (uint32_t)f->w_count, f->ncell, bump_step, f->stream);
+    f->launches += 3 + (f->w_count ? 1 : 0) + 1;
+    CUDA_TRY(cudaGetLastError());
+    f->n_read = f->w_count;  // single GPU: every WRITE entry is kept
+    f->w_count = 0;
+    return FLK_OK;
+}
+
+int enqueue_step(flk_field *f, uint64_t step, int use_step_dev, uint64_t seed, const float2 *d_inj, uint32_t n_inj) {
+    if (f->w_count + f->n_read > f->cap)
+        return fail(FLK_E_CAPACITY, "WRITE buffer would hold %llu objects, capacity is %llu",
+                    (unsigned long long)(f->w_count + f->n_read), (unsigned long long)f->cap);
+    StepArgs a;
+    a.cell_lo = 0; a.cell_hi = f->ncell;
+    a.step = step; a.use_step_dev = use_step_dev; a.seed = seed;
+    a.injected = d_inj; a.n_injected = n_inj;
+    a.out_base = (uint32_t)f->w_count;
+    a.math_mode = f->math_mode;
+    const bool prof = f->profile && !f->capturing;
+    if (prof) {
+        cudaEvent_t e0, e1;
+        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+        f->prof_events.push_back(e0); f->prof_events.push_back(e1);
+        CUDA_TRY(cudaEventRecord(e0, f->stream));
+    }
+    launch_step(f->g, f->p, f->s, a, (uint32_t)f->n_read, f->stream);
+    if (prof) CUDA_TRY(cudaEventRecord(f->prof_events.back(), f->stream));
+    if (f->n_read) f->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    f->w_count += f->n_read;
+    return FLK_OK;
+}
+
+}  // namespace flk
+
+using namespace flk;
+
+extern "C" {
+
+const char *flk_last_error(void) { return g_err.c_str(); }
+const char *flk_version(void) { return "flk 0.1 (sm_100a)"; }
+
+int flk_field_create(float width, float height, float discretization, int toroidal, uint64_t capacity, int device,
+                     flk_field **out) {
+    if (!out) return fail(FLK_E_INVALID, "out is null");
+    *out = nullptr;
+    if (capacity == 0 || capacity > 0x7fffffffull) return fail(FLK_E_INVALID, "capacity must be in [1, 2^31)");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(FLK_E_CUDA, "no CUDA device (%s): libflk has no CPU fallback", cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(FLK_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    flk_field *f = new flk_field();
+    f->device = device;
+    int rc = setup_geometry(f, width, height, discretization, toroidal);
+    if (rc) { delete f; return rc; }
+    f->p = Params{0.8f, 1.0f, 1.1f, 0.7f, 1.0f, 0.7f, 10.0f, 1, 1};  // flockers/src/main.rs:26-31, bird.rs:31
+    rc = update_window(f);
+    if (rc) { delete f; return rc; }
+    f->cap = capacity;
+    f->ncell = (uint32_t)f->g.ncols * (uint32_t)f->g.dh;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&f->ev0));
+    CUDA_TRY(cudaEventCreate(&f->ev1));
+    rc = field_alloc(f);
+    if (rc) { field_free(f); delete f; return rc; }
+    *out = f;
+    return FLK_OK;
+}
+
+int flk_field_destroy(flk_field *f) {
+    if (!f) return FLK_OK;
+    cudaSetDevice(f->device);
+    cudaStreamSynchronize(f->stream);
+    dist_free(f);
+    field_free(f);
+    delete f;
+    return FLK_OK;
+}
+
+int flk_field_clear(flk_field *f) {
+    CHECK_HANDLE(f);
+    const uint64_t m = (uint64_t)f->ncell + 1;
+    CUDA_TRY(cudaMemsetAsync(f->s.cell_start, 0, m * 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(f->s.cnt, 0, m * 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(f->s.n_read_dev, 0, 4, f->stream));
+    f->n_read = 0; f->w_count = 0;
+    f->pend_id.clear(); f->pend_loc.clear(); f->pend_ld.clear();
+    f->graph_valid = false;
+    return FLK_OK;
+}
+
+int flk_set_params(flk_field *f, float cohesion, float avoidance, float randomness, float consistency, float momentum,
+                   float jump, float radius, int relax) {
+    CHECK_HANDLE(f);
+    Params old = f->p;
+    f->p.cohesion = cohesion; f->p.avoidance = avoidance; f->p.randomness = randomness;
+    f->p.consistency = consistency; f->p.momentum = momentum; f->p.jump = jump;
+    f->p.radius = radius; f->p.relax = relax ? 1 : 0;
+    int rc = update_window(f);
+    if (rc) { f->p = old; return rc; }
+    f->graph_valid = false;
+    return FLK_OK;
+}
+
+int flk_set_math_mode(flk_field *f, int mode) {
+    CHECK_HANDLE(f);
+    if (mode != 0 && mode != 1) return fail(FLK_E_INVALID, "math mode must be 0 (exact) or 1 (fast)");
+    f->math_mode = mode;
+    f->graph_valid = false;
+    return FLK_OK;
+}
+
+int flk_field_dims(const flk_field *f, int32_t *dw, int32_t *dh, int32_t *mx, int32_t *my) {
+    if (!f) return fail(FLK_E_INVALID, "null handle");
+    if (dw) *dw = f->g.mx + 1;
+    if (dh) *dh = f->g.dh;
+    if (mx) *mx = f->g.mx;
+    if (my) *my = f->g.my;
+    return FLK_OK;
+}
+
+int flk_set_object_location(flk_field *f, uint32_t id, float x, float y, float last_dx, float last_dy) {
+    CHECK_HANDLE(f);
+    if (f->w_count + f->pend_id.size() + 1 > f->cap) return fail(FLK_E_CAPACITY, "capacity %llu exceeded", (unsigned long long)f->cap);
+    f->pend_id.push_back(id);
+    f->pend_loc.push_back(x); f->pend_loc.push_back(y);
+    f->pend_ld.push_back(last_dx); f->pend_ld.push_back(last_dy);
+    return FLK_OK;
+}
+
+int flk_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *last_d) {
+    CHECK_HANDLE(f);
+    if (n && (!id || !loc || !last_d)) return fail(FLK_E_INVALID, "null array");
+    int rc = flush_pending(f);
+    if (rc) return rc;
+    if (f->g.mode == 1) return dist_set_objects(f, n, id, loc, last_d);
+    return write_append(f, n, id, loc, last_d);
+}
+
+int flk_lazy_update(flk_field *f) {
+    CHECK_HANDLE(f);
+    int rc = flush_pending(f);
+    if (rc) return rc;
+    if (f->g.mode == 1) return fail(FLK_E_STATE, "dist handles fold lazy_update into flk_dist_step / flk_dist_commit");
+    CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+    rc = enqueue_lazy_update(f, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+    return FLK_OK;
+}
+
+int flk_step(flk_field *f, uint64_t step, uint64_t seed, const float *injected_r, uint64_t n_injected) {
+    CHECK_HANDLE(f);
+    int rc = flush_pending(f);
+    if (rc) return rc;
+    if (f->g.mode == 1) return fail(FLK_E_STATE, "use flk_dist_step on a dist handle");
+    const float2 *d_inj = nullptr;
+    if (injected_r) {
+        rc = upload_injected(f, injected_r, n_injected);
+        if (rc) return rc;
+        d_inj = f->d_injected;
+    }
+    CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+    rc = enqueue_step(f, step, 0, seed, d_inj, (uint32_t)n_injected);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+    return FLK_OK;
+}
+
+int flk_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed) {
+    CHECK_HANDLE(f);
+    int rc = flush_pending(f);
+    if (rc) return rc;
+    if (f->g.mode == 1) return dist_run(f, first_step, n_steps, seed);
+    if (f->w_count != 0) return fail(FLK_E_STATE, "flk_run needs an empty WRITE buffer (call flk_lazy_update first)");
+    CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+    if (f->profile || !f->use_graph) {
+        for (uint64_t t = 0; t < n_steps; ++t) {
+            rc = enqueue_step(f, first_step + t, 0, seed, nullptr, 0);
+            if (rc) return rc;
+            rc = enqueue_lazy_update(f, 0);
+            if (rc) return rc;
+        }
+    } else {
+        if (!f->graph_valid || f->graph_n != f->n_read || f->graph_seed != seed) {
+            if (f->graph_exec) { cudaGraphExecDestroy(f->graph_exec); f->graph_exec = nullptr; }
+            cudaGraph_t graph;
+            const uint64_t launches_before = f->launches;
+            CUDA_TRY(cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
+            f->capturing = true;
+            rc = enqueue_step(f, 0, 1, seed, nullptr, 0);
+            if (!rc) rc = enqueue_lazy_update(f, 1);
+            f->capturing = false;
+            cudaError_t ce = cudaStreamEndCapture(f->stream, &graph);
+            f->graph_launches = f->launches - launches_before;
+            f->launches = launches_before;
+            if (rc) return rc;
+            CUDA_TRY(ce);
+            CUDA_TRY(cudaGraphInstantiate(&f->graph_exec, graph, 0));
+            cudaGraphDestroy(graph);
+            f->graph_valid = true; f->graph_n = f->n_read; f->graph_seed = seed;
+        }
+        CUDA_TRY(cudaMemcpyAsync(f->s.step_dev, &first_step, 8, cudaMemcpyHostToDevice, f->stream));
+        for (uint64_t t = 0; t < n_steps; ++t) CUDA_TRY(cudaGraphLaunch(f->graph_exec, f->stream));
+        f->launches += f->graph_launches * n_steps;
+    }
+    CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+    return FLK_OK;
+}
+
+int flk_num_objects(const flk_field *f, uint64_t *n) {
+    if (!f || !n) return fail(FLK_E_INVALID, "null argument");
+    *n = f->n_read;
+    return FLK_OK;
+}
+
+int flk_snapshot(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n) {
+    CHECK_HANDLE(f);
+    if (f->g.mode == 1) { int rc = dist_refresh_counts(f); if (rc) return rc; }
+    const uint64_t nr = f->n_read;
+    if (n) *n = nr;
+    if (nr) {
+        float2 *d_loc = reinterpret_cast<float2 *>(f->scratch);
+        float2 *d_ld = d_loc + nr;
+        if (loc || last_d) {
+            launch_split(f->s, (uint32_t)nr, d_loc, d_ld, f->stream);
+            f->launches += 1;
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (id) CUDA_TRY(cudaMemcpyAsync(id, f->s.ids, nr * 4, cudaMemcpyDeviceToHost, f->stream));
+        if (loc) CUDA_TRY(cudaMemcpyAsync(loc, d_loc, nr * 8, cudaMemcpyDeviceToHost, f->stream));
+        if (last_d) CUDA_TRY(cudaMemcpyAsync(last_d, d_ld, nr * 8, cudaMemcpyDeviceToHost, f->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    return FLK_OK;
+}
+
+int flk_get_binning(flk_field *f, uint32_t *cell_start, uint32_t *sorted_ids) {
+    CHECK_HANDLE(f);
+    if (f->g.mode == 1) { int rc = dist_refresh_counts(f); if (rc) return rc; }
+    if (cell_start)
+        CUDA_TRY(cudaMemcpyAsync(cell_start, f->s.cell_start, ((uint64_t)f->ncell + 1) * 4, cudaMemcpyDeviceToHost, f->stream));
+    if (sorted_ids && f->n_read)
+        CUDA_TRY(cudaMemcpyAsync(sorted_ids, f->s.ids, f->n_read * 4, cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    return FLK_OK;
+}
+
+int flk_query_batch(flk_field *f, uint64_t nq, const float *loc, float dist, int relax, uint64_t *offsets,
+                    uint32_t *ids, uint64_t cap) {
+    CHECK_HANDLE(f);
+    if (!offsets || (nq && !loc)) return fail(FLK_E_INVALID, "null array");
+    if (nq > 0x7fffffffull) return fail(FLK_E_INVALID, "too many queries");
+    offsets[0] = 0;
+    if (nq == 0) return FLK_OK;
+    if (dist > 0.0f) {
+        const int k = (int)std::floor(dist / f->g.d);
+        if (f->g.toroidal && (2 * k + 1 > f->g.mx || 2 * k + 1 > f->g.my))
+            return fail(FLK_E_UNSUPPORTED, "query window wider than the grid");
+        if (f->g.mode == 1 && k > 1) return fail(FLK_E_UNSUPPORTED, "dist handles answer queries with k<=1 only");
+    }
+    float2 *d_loc = nullptr;
+    uint32_t *d_counts = nullptr, *d_out = nullptr;
+    uint64_t *d_off = nullptr;
+    int rc = FLK_OK;
+    std::vector<uint32_t> counts(nq);
+#define Q_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { rc = fail(FLK_E_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); goto done; } } while (0)
+    Q_TRY(cudaMalloc(&d_loc, nq * 8));
+    Q_TRY(cudaMalloc(&d_counts, nq * 4));
+    Q_TRY(cudaMalloc(&d_off, (nq + 1) * 8));
+    Q_TRY(cudaMemcpyAsync(d_loc, loc, nq * 8, cudaMemcpyHostToDevice, f->stream));
+    launch_query_count(f->g, f->s, (uint32_t)nq, d_loc, dist, relax, d_counts, f->stream);
+    f->launches += 1;
+    Q_TRY(cudaGetLastError());
+    Q_TRY(cudaMemcpyAsync(counts.data(), d_counts, nq * 4, cudaMemcpyDeviceToHost, f->stream));
+    Q_TRY(cudaStreamSynchronize(f->stream));
+    for (uint64_t q = 0; q < nq; ++q) offsets[q + 1] = offsets[q] + counts[q];
+    if (offsets[nq] > cap || (offsets[nq] && !ids)) {
+        rc = fail(FLK_E_CAPACITY, "query result has %llu ids, buffer holds %llu", (unsigned long long)offsets[nq], (unsigned long long)cap);
+        goto done;
+    }
+    if (offsets[nq]) {
+        Q_TRY(cudaMalloc(&d_out, offsets[nq] * 4));
+        Q_TRY(cudaMemcpyAsync(d_off, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, f->stream));
+        launch_query_fill(f->g, f->s, (uint32_t)nq, d_loc, dist, relax, d_off, d_out, f->stream);
+        f->launches += 1;
+        Q_TRY(cudaGetLastError());
+        Q_TRY(cudaMemcpyAsync(ids, d_out, offsets[nq] * 4, cudaMemcpyDeviceToHost, f->stream));
+        Q_TRY(cudaStreamSynchronize(f->stream));
+    }
+done:
+#undef Q_TRY
+    cudaFree(d_loc); cudaFree(d_counts); cudaFree(d_off); cudaFree(d_out);
+    return rc;
+}
+
+static int query_one(flk_field *f, float x, float y, float dist, int relax, uint32_t *ids, uint32_t cap, uint32_t *n) {
+    CHECK_HANDLE(f);
+    if (!n) return fail(FLK_E_INVALID, "n is null");
+    const float loc[2] = {x, y};
+    uint64_t off[2] = {0, 0};
+    // first try with the caller's buffer; on overflow report the full size with the first `cap` ids
+    int rc = flk_query_batch(f, 1, loc, dist, relax, off, ids, cap);
+    *n = (uint32_t)off[1];
+    if (rc == FLK_E_CAPACITY && off[1] > cap) {
+        std::vector<uint32_t> tmp(off[1]);
+        int rc2 = flk_query_batch(f, 1, loc, dist, relax, off, tmp.data(), tmp.size());
+        if (rc2) return rc2;
+        if (ids && cap) memcpy(ids, tmp.data(), (size_t)cap * 4);
+        return fail(FLK_E_CAPACITY, "query result has %u ids, buffer holds %u", *n, cap);
+    }
+    return rc;
+}
+
+int flk_get_neighbors_within_relax_distance(flk_field *f, float x, float y, float dist, uint32_t *ids, uint32_t cap,
+                                            uint32_t *n) {
+    return query_one(f, x, y, dist, 1, ids, cap, n);
+}
+
+int flk_get_neighbors_within_distance(flk_field *f, float x, float y, float dist, uint32_t *ids, uint32_t cap,
+                                      uint32_t *n) {
+    return query_one(f, x, y, dist, 0, ids, cap, n);
+}
+
+int flk_synchronize(flk_field *f) {
+    CHECK_HANDLE(f);
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    return FLK_OK;
+}
+
+int flk_elapsed_ms(flk_field *f, float *ms) {
+    CHECK_HANDLE(f);
+    if (!ms) return fail(FLK_E_INVALID, "ms is null");
+    CUDA_TRY(cudaEventSynchronize(f->ev1));
+    CUDA_TRY(cudaEventElapsedTime(ms, f->ev0, f->ev1));
+    return FLK_OK;
+}
+
+int flk_stream(flk_field *f, void **stream) {
+    if (!f || !stream) return fail(FLK_E_INVALID, "null argument");
+    *stream = (void *)f->stream;
+    return FLK_OK;
+}
+
+int flk_launch_count(const flk_field *f, uint64_t *n) {
+    if (!f || !n) return fail(FLK_E_INVALID, "null argument");
+    *n = f->launches;
+    return FLK_OK;
+}
+
+int flk_profile_enable(flk_field *f, int on) {
+    CHECK_HANDLE(f);
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    for (auto &e : f->prof_events) cudaEventDestroy(e);
+    f->prof_events.clear();
+    f->profile = on != 0;
+    return FLK_OK;
+}
+
+int flk_profile_step_kernel(flk_field *f, double *total_ms, uint64_t *launches) {
+    CHECK_HANDLE(f);
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < f->prof_events.size(); i += 2) {
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, f->prof_events[i], f->prof_events[i + 1]));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = f->prof_events.size() / 2;
+    return FLK_OK;
+}
+
+int flk_use_graph(flk_field *f, int on) {
+    CHECK_HANDLE(f);
+    f->use_graph = on != 0;
+    return FLK_OK;
+}
+
+int flk_host_alloc(void **p, uint64_t bytes) {
+    if (!p) return fail(FLK_E_INVALID, "p is null");
+    CUDA_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return FLK_OK;
+}
+
+int flk_host_free(void *p) {
+    CUDA_TRY(cudaFreeHost(p));
+    return FLK_OK;
+}
+
+}  // extern "C"
+
+namespace flk {
+
+int upload_injected(flk_field *f, const float *r, uint64_t n) {
+    if (n == 0) return FLK_OK;
+    if (n > f->injected_cap) {
+        if (f->d_injected) { CUDA_TRY(cudaStreamSynchronize(f->stream)); cudaFree(f->d_injected); f->d_injected = nullptr; }
+        CUDA_TRY(cudaMalloc(&f->d_injected, n * 8));
+        f->injected_cap = n;
+    }
+    CUDA_TRY(cudaMemcpyAsync(f->d_injected, r, n * 8, cudaMemcpyHostToDevice, f->stream));
+    return FLK_OK;
+}
+
+}  // namespace flk

@@ -1,0 +1,71 @@
+// flk_internal.cuh — the handle behind `flk_field*` and helpers shared by flk_api.cu / flk_dist.cu.
+#pragma once
+#include <cstdarg>
+#include <string>
+#include <vector>
+
+#include "flk_kernels.cuh"
+
+struct flk_dist_state;  // flk_dist.cu
+
+struct flk_field {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    flk::Geom g{};
+    flk::Params p{};
+    int math_mode = 0;
+    uint64_t cap = 0;
+    uint32_t ncell = 0;      // local cells = ncols*dh
+    flk::Store s{};
+    uint8_t *scratch = nullptr;
+    uint64_t n_read = 0;     // objects in the READ buffer (host view; an upper bound on dist handles)
+    uint64_t w_count = 0;    // WRITE slots in use
+    std::vector<uint32_t> pend_id;   // buffered single set_object_location calls
+    std::vector<float> pend_loc, pend_ld;
+    float2 *d_injected = nullptr;
+    uint64_t injected_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // flk_run graph cache
+    bool use_graph = true, graph_valid = false, capturing = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t graph_n = 0, graph_seed = 0, graph_launches = 0;
+    uint64_t launches = 0;
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;
+    flk_dist_state *dist = nullptr;
+};
+
+namespace flk {
+
+int fail(int code, const char *fmt, ...);
+
+#define CUDA_TRY(x)                                                                                     \
+    do {                                                                                                \
+        cudaError_t e_ = (x);                                                                           \
+        if (e_ != cudaSuccess) return flk::fail(FLK_E_CUDA, "%s: %s", #x, cudaGetErrorString(e_));      \
+    } while (0)
+
+#define CHECK_HANDLE(f)                                                                                 \
+    do {                                                                                                \
+        if (!(f)) return flk::fail(FLK_E_INVALID, "null handle");                                       \
+        cudaError_t e_ = cudaSetDevice((f)->device);                                                    \
+        if (e_ != cudaSuccess) return flk::fail(FLK_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e_)); \
+    } while (0)
+
+int setup_geometry(flk_field *f, float w, float h, float d, int toroidal);
+int update_window(flk_field *f);
+int field_alloc(flk_field *f);
+void field_free(flk_field *f);
+int flush_pending(flk_field *f);
+int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld);
+int upload_injected(flk_field *f, const float *r, uint64_t n);
+int enqueue_step(flk_field *f, uint64_t step, int use_step_dev, uint64_t seed, const float2 *d_inj, uint32_t n_inj);
+int enqueue_lazy_update(flk_field *f, int bump_step);
+
+// flk_dist.cu
+void dist_free(flk_field *f);
+int dist_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld);
+int dist_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed);
+int dist_refresh_counts(flk_field *f);
+
+}  // namespace flk

@@ -1,0 +1,449 @@
+// flk_kernels.cu — sm_100a kernels of the Flockers hot path.
+//
+//   k_step      Bird::step for every bird of the READ buffer (flockers/src/model/bird.rs:27-145), fused with
+//               Field2D::set_object_location (cell key + per-cell arrival slot of the successor, bird.rs:142-144)
+//   k_scan_*    exclusive scan of the per-cell counters  -> cell_start            } Field2D::lazy_update
+//   k_scatter   counting-sort scatter of (id, source index) into cell order       } (flockers/src/model/state.rs:54-56)
+//   k_rank      ascending-id rank inside each cell + gather of the records        }
+//   k_ingest    bulk Field2D::set_object_location from host arrays (state.rs:49)
+//   k_query_*   Field2D::get_neighbors_within_{relax_,}distance (bird.rs:29-31)
+//
+// No tensor cores: the path has no dense contraction.
+#include "flk_kernels.cuh"
+
+namespace flk {
+
+// ------------------------------------------------------------------------------------------------
+// neighbour window enumeration: calls f(s, e) for each run [s,e) of READ indices, in the reference's
+// query order (x-outer, y-inner, bag order; SURVEY Appendix B "relax query")
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void for_each_window_run(const Geom &g, const uint32_t *__restrict__ cell_start,
+                                                    int lc, int cy, int k, F &&f) {
+    for (int ox = -k; ox <= k; ++ox) {
+        const int col = window_col(g, lc, ox);
+        if (col < 0) continue;
+        int r0 = cy - k, r1 = cy + k;
+        bool contiguous;
+        if (g.toroidal) {
+            contiguous = (r0 >= 0) && (r1 < g.my);
+        } else {
+            r0 = max(r0, 0);
+            r1 = min(r1, g.dh - 1);
+            contiguous = true;
+        }
+        const int ngroups = contiguous ? 1 : (2 * k + 1);
+        const uint32_t *cs = cell_start + (size_t)col * g.dh;
+        for (int gi = 0; gi < ngroups; ++gi) {
+            int ra, rb;
+            if (contiguous) {
+                ra = r0; rb = r1;
+            } else {
+                ra = rb = wrap_row(g, cy - k + gi);
+                if (ra < 0) continue;
+            }
+            f(__ldg(cs + ra), __ldg(cs + rb + 1));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_step
+// ------------------------------------------------------------------------------------------------
+template <bool RELAX, int MATH>
+__global__ void __launch_bounds__(128) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
+    const uint32_t lo = __ldg(s.cell_start + a.cell_lo);
+    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
+    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+
+    const Rec me = s.rec[i];
+    const uint32_t my_id = s.ids[i];
+    const float W = g.W, H = g.H;
+    const float halfW = __fdiv_rn(W, 2.0f), halfH = __fdiv_rn(H, 2.0f);
+
+    // cell of this bird (same arithmetic as the binning that placed it)
+    const int gcx = cell_coord(me.x, g.d, g.mx + 1);
+    const int cy = cell_coord(me.y, g.d, g.dh);
+    const int lc = local_col(g, gcx);
+
+    float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;  // bird.rs:44-49
+    uint32_t nvec = 0;   // size of the query result (bird.rs:42 tests emptiness)
+    int count = 0;       // bird.rs:50
+
+    for_each_window_run(g, s.cell_start, lc, cy, p.k, [&](uint32_t rs, uint32_t re) {
+        uint32_t j = rs;
+        while (true) {
+            // the caller itself is part of the query result and skipped by id (bird.rs:53): split the run at i
+            const uint32_t stop = (RELAX && i >= j && i < re) ? i : re;
+#pragma unroll 2
+            for (; j < stop; ++j) {
+                const float4 o = __ldg(reinterpret_cast<const float4 *>(s.rec) + j);
+                const float dx = toroidal_distance(me.x, o.x, W, halfW);   // bird.rs:54
+                const float dy = toroidal_distance(me.y, o.y, H, halfH);   // bird.rs:55
+                const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));  // :59
+                if (!RELAX) {
+                    // get_neighbors_within_distance keeps elem iff sqrt(dx^2+dy^2) <= dist
+                    float qs = sq;
+                    if (!g.toroidal) {
+                        const float px = __fadd_rn(me.x, -o.x), py = __fadd_rn(me.y, -o.y);
+                        qs = __fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py));
+                    }
+                    if (!(__fsqrt_rn(qs) <= p.radius)) continue;
+                    ++nvec;
+                    if (j == i) continue;
+                    ++count;
+                }
+                const float den = __fadd_rn(__fmul_rn(sq, sq), 1.0f);
+                if (MATH == 0) {
+                    xa = __fadd_rn(xa, __fdiv_rn(dx, den));   // :60
+                    ya = __fadd_rn(ya, __fdiv_rn(dy, den));   // :61
+                } else {
+                    const float inv = __frcp_rn(den);
+                    xa = __fadd_rn(xa, __fmul_rn(dx, inv));
+                    ya = __fadd_rn(ya, __fmul_rn(dy, inv));
+                }
+                xc = __fadd_rn(xc, dx);      // :64
+                yc = __fadd_rn(yc, dy);      // :65
+                xs = __fadd_rn(xs, o.z);     // :68
+                ys = __fadd_rn(ys, o.w);     // :69
+            }
+            if (stop == re) break;
+            j = stop + 1;
+        }
+        if (RELAX) {
+            nvec += re - rs;
+            count += (int)(re - rs) - ((i >= rs && i < re) ? 1 : 0);
+        }
+    });
+
+    float avo_x = 0.0f, avo_y = 0.0f, coh_x = 0.0f, coh_y = 0.0f;   // bird.rs:36-40
+    float rnd_x = 0.0f, rnd_y = 0.0f, con_x = 0.0f, con_y = 0.0f;
+    if (nvec != 0) {                                                  // :42
+        if (count > 0) {                                              // :73
+            const float c = (float)count;
+            xa = __fdiv_rn(xa, c); ya = __fdiv_rn(ya, c);             // :74-75
+            xc = __fdiv_rn(xc, c); yc = __fdiv_rn(yc, c);             // :76-77
+            xs = __fdiv_rn(xs, c); ys = __fdiv_rn(ys, c);             // :78-79
+            con_x = __fdiv_rn(xs, c); con_y = __fdiv_rn(ys, c);       // :81-84 (second division, kept)
+        } else {
+            con_x = xs; con_y = ys;                                   // :85-90
+        }
+        avo_x = __fmul_rn(400.0f, xa); avo_y = __fmul_rn(400.0f, ya); // :92-95
+        coh_x = __fdiv_rn(-xc, 10.0f); coh_y = __fdiv_rn(-yc, 10.0f); // :97-100
+        float r1, r2;                                                 // :103-107
+        if (a.injected != nullptr && my_id < a.n_injected) {
+            const float2 r = __ldg(a.injected + my_id);
+            r1 = r.x; r2 = r.y;
+        } else {
+            const uint64_t step = a.use_step_dev ? *s.step_dev : a.step;
+            uint32_t o0, o1;
+            philox4x32_10(my_id, (uint32_t)step, (uint32_t)(step >> 32), 0u, (uint32_t)a.seed,
+                          (uint32_t)(a.seed >> 32), o0, o1);
+            r1 = u32_to_unit(o0); r2 = u32_to_unit(o1);
+        }
+        const float xr = __fadd_rn(__fmul_rn(r1, 2.0f), -1.0f);
+        const float yr = __fadd_rn(__fmul_rn(r2, 2.0f), -1.0f);
+        const float sq = __fsqrt_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(yr, yr)));   // :109
+        rnd_x = __fdiv_rn(__fmul_rn(0.05f, xr), sq);                  // :110-113
+        rnd_y = __fdiv_rn(__fmul_rn(0.05f, yr), sq);
+    }
+    // :116-127, summed left to right
+    float dx = __fmul_rn(p.cohesion, coh_x);
+    dx = __fadd_rn(dx, __fmul_rn(p.avoidance, avo_x));
+    dx = __fadd_rn(dx, __fmul_rn(p.consistency, con_x));
+    dx = __fadd_rn(dx, __fmul_rn(p.randomness, rnd_x));
+    dx = __fadd_rn(dx, __fmul_rn(p.momentum, me.ldx));
+    float dy = __fmul_rn(p.cohesion, coh_y);
+    dy = __fadd_rn(dy, __fmul_rn(p.avoidance, avo_y));
+    dy = __fadd_rn(dy, __fmul_rn(p.consistency, con_y));
+    dy = __fadd_rn(dy, __fmul_rn(p.randomness, rnd_y));
+    dy = __fadd_rn(dy, __fmul_rn(p.momentum, me.ldy));
+    const float dis = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));   // :129
+    if (dis > 0.0f) {                                                                // :130
+        dx = __fmul_rn(__fdiv_rn(dx, dis), p.jump);                                  // :131
+        dy = __fmul_rn(__fdiv_rn(dy, dis), p.jump);                                  // :132
+    }
+    Rec out;
+    out.ldx = dx; out.ldy = dy;                                                      // :135
+    out.x = toroidal_transform(__fadd_rn(me.x, dx), W);                              // :137
+    out.y = toroidal_transform(__fadd_rn(me.y, dy), H);                              // :138
+
+    // Field2D::set_object_location(*self, loc) (:142-144): WRITE buffer entry i + cell counter
+    const int ncx = cell_coord(out.x, g.d, g.mx + 1);
+    const int ncy = cell_coord(out.y, g.d, g.dh);
+    const int nlc = local_col(g, ncx);
+    uint32_t key = KEY_INVALID, slot = 0;
+    if (nlc != FLK_DROP) {
+        key = (uint32_t)nlc * (uint32_t)g.dh + (uint32_t)ncy;
+        slot = atomicAdd(s.cnt + key, 1u);
+    }
+    const uint32_t w = a.out_base + i;
+    reinterpret_cast<float4 *>(s.trec)[w] = make_float4(out.x, out.y, out.ldx, out.ldy);
+    s.tid[w] = my_id;
+    s.tkey[w] = key;
+    s.tslot[w] = slot;
+}
+
+void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
+                 cudaStream_t st) {
+    if (n_upper == 0) return;
+    const dim3 block(128), grid((n_upper + 127) / 128);
+    if (p.relax) {
+        if (a.math_mode == 0) k_step<true, 0><<<grid, block, 0, st>>>(g, p, s, a);
+        else k_step<true, 1><<<grid, block, 0, st>>>(g, p, s, a);
+    } else {
+        if (a.math_mode == 0) k_step<false, 0><<<grid, block, 0, st>>>(g, p, s, a);
+        else k_step<false, 1><<<grid, block, 0, st>>>(g, p, s, a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_ingest: bulk set_object_location from (already uploaded) arrays; appends at WRITE index base+j
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ingest(const Geom g, const Store s, uint32_t n, const uint32_t *__restrict__ id,
+                                                const float2 *__restrict__ loc, const float2 *__restrict__ ld,
+                                                uint32_t base) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float2 l = loc[j], d = ld[j];
+    const int cx = cell_coord(l.x, g.d, g.mx + 1);
+    const int cy = cell_coord(l.y, g.d, g.dh);
+    const int lc = local_col(g, cx);
+    uint32_t key = KEY_INVALID, slot = 0;
+    if (lc != FLK_DROP) {
+        key = (uint32_t)lc * (uint32_t)g.dh + (uint32_t)cy;
+        slot = atomicAdd(s.cnt + key, 1u);
+    }
+    reinterpret_cast<float4 *>(s.trec)[base + j] = make_float4(l.x, l.y, d.x, d.y);
+    s.tid[base + j] = id[j];
+    s.tkey[base + j] = key;
+    s.tslot[base + j] = slot;
+}
+
+void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id, const float2 *loc,
+                   const float2 *ld, uint32_t base, cudaStream_t st) {
+    if (n == 0) return;
+    k_ingest<<<(n + 255) / 256, 256, 0, st>>>(g, s, n, id, loc, ld, base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of cnt[0..m) -> cell_start[0..m), zeroing cnt (reduce / spine / down-sweep)
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, total in *total
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t wsum[THREADS / 32];
+    __shared__ uint32_t wtot;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t inc = warp_inclusive_scan(v);
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t x = lane < THREADS / 32 ? wsum[lane] : 0;
+        uint32_t xi = warp_inclusive_scan(x);
+        if (lane < THREADS / 32) wsum[lane] = xi - x;
+        if (lane == 31) wtot = xi;
+    }
+    __syncthreads();
+    const uint32_t r = inc - v + wsum[w];
+    *total = wtot;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t *__restrict__ cnt, uint32_t m,
+                                                              uint32_t *__restrict__ blocksum) {
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t)
+        if (base + t < m) v += cnt[base + t];
+    uint32_t total;
+    block_exclusive_scan<SCAN_THREADS>(v, &total);
+    if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_spine(uint32_t *__restrict__ blocksum, uint32_t nblk) {
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nblk; base += 1024) {
+        const uint32_t idx = base + threadIdx.x;
+        const uint32_t v = idx < nblk ? blocksum[idx] : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan<1024>(v, &total);
+        if (idx < nblk) blocksum[idx] = ex + carry;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(uint32_t *__restrict__ cnt, uint32_t m,
+                                                            const uint32_t *__restrict__ blocksum,
+                                                            uint32_t *__restrict__ cell_start) {
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t item[SCAN_ITEMS];
+    uint32_t v = 0;
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) {
+        item[t] = (base + t < m) ? cnt[base + t] : 0;
+        v += item[t];
+    }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan<SCAN_THREADS>(v, &total) + blocksum[blockIdx.x];
+#pragma unroll
+    for (int t = 0; t < SCAN_ITEMS; ++t) {
+        if (base + t < m) {
+            cell_start[base + t] = run;
+            cnt[base + t] = 0;   // the new WRITE buffer starts empty (lazy_update clears the bags)
+        }
+        run += item[t];
+    }
+}
+
+void launch_scan(const Store &s, uint32_t m, cudaStream_t st) {
+    const uint32_t nblk = (m + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_reduce<<<nblk, SCAN_THREADS, 0, st>>>(s.cnt, m, s.blocksum);
+    k_scan_spine<<<1, 1024, 0, st>>>(s.blocksum, nblk);
+    k_scan_down<<<nblk, SCAN_THREADS, 0, st>>>(s.cnt, m, s.blocksum, s.cell_start);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_scatter / k_rank: WRITE buffer -> READ buffer in (cell, ascending id) order
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t key = s.tkey[i];
+    if (key == KEY_INVALID) return;
+    const uint32_t p = s.cell_start[key] + s.tslot[i];
+    s.sid[p] = s.tid[i];
+    s.ssrc[p] = i;
+    s.skey[p] = key;
+}
+
+void launch_scatter(const Store &s, uint32_t n, cudaStream_t st) {
+    if (n == 0) return;
+    k_scatter<<<(n + 255) / 256, 256, 0, st>>>(s, n);
+}
+
+__global__ void __launch_bounds__(256) k_rank(const Store s, uint32_t ncell, int bump_step) {
+    const uint32_t n = s.cell_start[ncell];
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) {
+        *s.n_read_dev = n;
+        if (bump_step) *s.step_dev += 1;
+    }
+    if (p >= n) return;
+    const uint32_t key = s.skey[p];
+    const uint32_t lo = s.cell_start[key], hi = s.cell_start[key + 1];
+    const uint32_t my_id = s.sid[p];
+    uint32_t r = 0;
+    for (uint32_t q = lo; q < hi; ++q) {
+        const uint32_t other = s.sid[q];
+        r += (other < my_id) || (other == my_id && q < p);
+    }
+    const uint32_t dst = lo + r;
+    reinterpret_cast<float4 *>(s.rec)[dst] = reinterpret_cast<const float4 *>(s.trec)[s.ssrc[p]];
+    s.ids[dst] = my_id;
+}
+
+void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st) {
+    const uint32_t nb = n_upper == 0 ? 1 : (n_upper + 255) / 256;
+    k_rank<<<nb, 256, 0, st>>>(s, ncell, bump_step);
+}
+
+__global__ void __launch_bounds__(256) k_fill_u32(uint32_t *p, uint32_t v, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+void launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t st) {
+    if (n == 0) return;
+    k_fill_u32<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, v, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// snapshot helper: split READ records into loc / last_d arrays
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_split(const Store s, uint32_t n, float2 *loc, float2 *ld) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 r = reinterpret_cast<const float4 *>(s.rec)[i];
+    if (loc) loc[i] = make_float2(r.x, r.y);
+    if (ld) ld[i] = make_float2(r.z, r.w);
+}
+
+void launch_split(const Store &s, uint32_t n, float2 *loc, float2 *ld, cudaStream_t st) {
+    if (n == 0) return;
+    k_split<<<(n + 255) / 256, 256, 0, st>>>(s, n, loc, ld);
+}
+
+// ------------------------------------------------------------------------------------------------
+// queries (Field2D::get_neighbors_within_{relax_,}distance): one thread per query location
+// ------------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_query(const Geom g, const Store s, uint32_t nq, const float2 *__restrict__ loc,
+                                               float dist, int relax, uint32_t *__restrict__ counts,
+                                               const uint64_t *__restrict__ offsets, uint32_t *__restrict__ out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const float2 l = loc[q];
+    uint32_t n = 0;
+    if (dist > 0.0f) {
+        const int k = __float2int_rz(floorf(__fdiv_rn(dist, g.d)));
+        const int gcx = cell_coord(l.x, g.d, g.mx + 1);
+        const int cy = cell_coord(l.y, g.d, g.dh);
+        const int lc = local_col(g, gcx);
+        const float halfW = __fdiv_rn(g.W, 2.0f), halfH = __fdiv_rn(g.H, 2.0f);
+        uint32_t *dst = FILL ? out + offsets[q] : nullptr;
+        if (lc != FLK_DROP) {
+            for_each_window_run(g, s.cell_start, lc, cy, k, [&](uint32_t rs, uint32_t re) {
+                for (uint32_t j = rs; j < re; ++j) {
+                    if (!relax) {
+                        const float4 o = reinterpret_cast<const float4 *>(s.rec)[j];
+                        float dx, dy;
+                        if (g.toroidal) {
+                            dx = toroidal_distance(l.x, o.x, g.W, halfW);
+                            dy = toroidal_distance(l.y, o.y, g.H, halfH);
+                        } else {
+                            dx = __fadd_rn(l.x, -o.x);
+                            dy = __fadd_rn(l.y, -o.y);
+                        }
+                        const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                        if (!(__fsqrt_rn(sq) <= dist)) continue;
+                    }
+                    if (FILL) dst[n] = s.ids[j];
+                    ++n;
+                }
+            });
+        }
+    }
+    if (!FILL) counts[q] = n;
+}
+
+void launch_query_count(const Geom &g, const Store &s, uint32_t nq, const float2 *loc, float dist, int relax,
+                        uint32_t *counts, cudaStream_t st) {
+    if (nq == 0) return;
+    k_query<false><<<(nq + 127) / 128, 128, 0, st>>>(g, s, nq, loc, dist, relax, counts, nullptr, nullptr);
+}
+
+void launch_query_fill(const Geom &g, const Store &s, uint32_t nq, const float2 *loc, float dist, int relax,
+                       const uint64_t *offsets, uint32_t *out, cudaStream_t st) {
+    if (nq == 0) return;
+    k_query<true><<<(nq + 127) / 128, 128, 0, st>>>(g, s, nq, loc, dist, relax, nullptr, offsets, out);
+}
+
+}  // namespace flk

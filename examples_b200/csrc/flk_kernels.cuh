@@ -1,0 +1,54 @@
+// flk_kernels.cuh — launch interface between the C-ABI layer (flk_api.cu) and the kernels (flk_kernels.cu).
+#pragma once
+#include "flk_device.cuh"
+
+namespace flk {
+
+constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
+
+// All device arrays of one handle (DESIGN.md §data layout).  READ buffer = (rec, ids, cell_start), sorted by
+// (cell, id).  WRITE buffer = (trec, tid, tkey, tslot) + per-cell counters cnt, in arrival order.
+struct Store {
+    Rec *rec;              // READ records
+    uint32_t *ids;         // READ ids
+    uint32_t *cell_start;  // READ: ncell+1 offsets
+    Rec *trec;             // WRITE records
+    uint32_t *tid;         // WRITE ids
+    uint32_t *tkey;        // WRITE local cell key (KEY_INVALID = not kept on this GPU)
+    uint32_t *tslot;       // WRITE arrival slot inside its cell
+    uint32_t *cnt;         // WRITE per-cell counters (ncell+1)
+    uint32_t *sid;         // staging for the (cell,id) ranking
+    uint32_t *ssrc;
+    uint32_t *skey;
+    uint32_t *blocksum;    // scan scratch
+    uint64_t *step_dev;    // tick counter used by graph replays
+    uint32_t *n_read_dev;  // number of READ objects (device copy)
+};
+
+struct StepArgs {
+    uint32_t cell_lo, cell_hi;  // step birds of cells [cell_lo, cell_hi)
+    uint64_t step;              // tick number (ignored when use_step_dev)
+    int use_step_dev;
+    uint64_t seed;
+    const float2 *injected;     // device, indexed by id, or null
+    uint32_t n_injected;        // pairs in `injected`
+    uint32_t out_base;          // WRITE index of READ index 0
+    int math_mode;              // 0 exact, 1 fast
+};
+
+void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id, const float2 *loc,
+                   const float2 *ld, uint32_t base, cudaStream_t st);
+void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
+                 cudaStream_t st);
+// exclusive scan of cnt -> cell_start, zeroing cnt; 3 launches
+void launch_scan(const Store &s, uint32_t ncell_plus1, cudaStream_t st);
+void launch_scatter(const Store &s, uint32_t n_write_extent, cudaStream_t st);
+void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st);
+void launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t st);
+void launch_split(const Store &s, uint32_t n, float2 *loc, float2 *ld, cudaStream_t st);
+void launch_query_count(const Geom &g, const Store &s, uint32_t nq, const float2 *loc, float dist, int relax,
+                        uint32_t *counts, cudaStream_t st);
+void launch_query_fill(const Geom &g, const Store &s, uint32_t nq, const float2 *loc, float dist, int relax,
+                       const uint64_t *offsets, uint32_t *out, cudaStream_t st);
+
+}  // namespace flk

@@ -1,0 +1,173 @@
+/*
+ * flk.h — C ABI of the B200-native Flockers hot path (libflk.so).
+ *
+ * This is the drop-in boundary: the entry points are what a krABMaga `Field2D<Bird>` /
+ * `Flocker` binding needs (Rust `extern "C"`, see INTEGRATION.md and rust/src/ffi.rs).
+ * Plain C types only: opaque handle, pointers, sizes.  No torch types, no callbacks.
+ *
+ * Citations are relative to the reference checkout (krABMaga/examples):
+ *   flockers/src/model/bird.rs      Bird::step                      (a5..a10 in SURVEY.md §8)
+ *   flockers/src/model/state.rs     Flocker::{new,init,update}       (a2,a3,a11)
+ *   flockers_mpi/src/model/*.rs     halo / migration protocol        (a13)
+ * Engine methods (Field2D::*) live in the external crate krabmaga 0.5.*; their call sites are cited.
+ *
+ * Conventions
+ *   - every call returns FLK_OK (0) or a negative FLK_E_* code; nothing throws or aborts across
+ *     the boundary; flk_last_error() returns a thread-local description of the last failure.
+ *   - a handle is driven by ONE host thread (like krABMaga's Schedule); distinct handles are independent.
+ *   - the library owns all device memory; host arrays passed in stay owned by the caller.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with FLK_E_CUDA.
+ *   - `float2`-shaped arguments are plain `const float*` with x,y interleaved (Real2D{x,y}).
+ */
+#ifndef FLK_H
+#define FLK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define FLK_OK 0
+#define FLK_E_INVALID (-1)     /* bad argument / null handle */
+#define FLK_E_CUDA (-2)        /* CUDA runtime error (message in flk_last_error) */
+#define FLK_E_CAPACITY (-3)    /* more objects than the capacity given at create / output truncated */
+#define FLK_E_UNSUPPORTED (-4) /* configuration outside what the kernels implement */
+#define FLK_E_NCCL (-5)        /* NCCL error / library not found */
+#define FLK_E_STATE (-6)       /* call not valid in the current state */
+
+typedef struct flk_field flk_field;
+
+/* ---- lifecycle ----------------------------------------------------------------------------- */
+
+/* Field2D::new(width, height, discretization, toroidal)           flockers/src/model/state.rs:24
+ * capacity = max number of objects the field will ever hold; device = CUDA ordinal. */
+int flk_field_create(float width, float height, float discretization, int toroidal,
+                     uint64_t capacity, int device, flk_field **out);
+int flk_field_destroy(flk_field *f);
+
+/* State::reset re-creates the field (flockers/src/model/state.rs:32-35): drop every object, keep memory. */
+int flk_field_clear(flk_field *f);
+
+/* model constants COHESION..JUMP (flockers/src/main.rs:26-31), query radius (bird.rs:31), and which
+ * query Bird::step uses: relax=1 get_neighbors_within_relax_distance (shipped, bird.rs:29-31),
+ * relax=0 get_neighbors_within_distance.  Defaults are the reference values. */
+int flk_set_params(flk_field *f, float cohesion, float avoidance, float randomness, float consistency,
+                   float momentum, float jump, float radius, int relax);
+
+/* 0 = exact (default): IEEE f32, no FMA contraction — bit-identical to the reference arithmetic.
+ * 1 = fast: reciprocal-based division in the neighbour loop (<= 2 ulp per term, same order). */
+int flk_set_math_mode(flk_field *f, int mode);
+
+/* grid geometry: allocated cells dw x dh (= ceil(W/d)+1, one slack row/col) and wrap modulus mx x my */
+int flk_field_dims(const flk_field *f, int32_t *dw, int32_t *dh, int32_t *mx, int32_t *my);
+
+/* ---- Field2D write side ------------------------------------------------------------------------- */
+
+/* Field2D::set_object_location(bird, loc)   flockers/src/model/state.rs:49, bird.rs:142-144
+ * Appends Bird{id, loc, last_d} to the WRITE buffer; visible to queries after flk_lazy_update. */
+int flk_set_object_location(flk_field *f, uint32_t id, float x, float y, float last_dx, float last_dy);
+
+/* bulk form of the above (n birds; HOST arrays; loc/last_d interleaved x,y) */
+int flk_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *last_d);
+
+/* Field::lazy_update()   flockers/src/model/state.rs:54-56
+ * WRITE becomes READ (re-binned by cell, ascending id inside a cell), the new WRITE buffer is empty.
+ * Asynchronous on the handle's stream. */
+int flk_lazy_update(flk_field *f);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+
+/* One tick of `for every scheduled Bird: Bird::step(state)` (flockers/src/model/bird.rs:27-145):
+ * reads the READ buffer, appends every bird's successor to the WRITE buffer.
+ * Randomness (bird.rs:103-107): if injected_r != NULL it is a HOST array of n_injected (r1,r2) pairs,
+ * the pair of bird `id` at [2*id],[2*id+1] (ids >= n_injected fall back to Philox);
+ * else Philox4x32-10 with key=seed, counter=(id,step,0), r = (out >> 8) * 2^-24.
+ * Asynchronous on the handle's stream (injected_r is copied before returning). */
+int flk_step(flk_field *f, uint64_t step, uint64_t seed, const float *injected_r, uint64_t n_injected);
+
+/* `simulate!(state, n_steps, 1)` inner loop (flockers/src/main.rs:47): n_steps x { step ; lazy_update },
+ * tick numbers first_step, first_step+1, ...; Philox randomness.  Replays a captured CUDA graph. */
+int flk_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed);
+
+/* ---- Field2D read side ------------------------------------------------------------------------- */
+
+/* Field2D::get_neighbors_within_relax_distance(loc, dist)   flockers/src/model/bird.rs:29-31
+ * Field2D::get_neighbors_within_distance(loc, dist)         (named by the engine API; not called by bird.rs)
+ * Synchronous.  Writes up to `cap` ids in query order (x-outer, y-inner, ascending id per cell);
+ * *n = full result size; returns FLK_E_CAPACITY if *n > cap (first cap ids are valid). */
+int flk_get_neighbors_within_relax_distance(flk_field *f, float x, float y, float dist,
+                                            uint32_t *ids, uint32_t cap, uint32_t *n);
+int flk_get_neighbors_within_distance(flk_field *f, float x, float y, float dist,
+                                      uint32_t *ids, uint32_t cap, uint32_t *n);
+
+/* batched query for nq HOST locations (interleaved x,y): offsets[nq+1], ids[cap] (CSR) */
+int flk_query_batch(flk_field *f, uint64_t nq, const float *loc, float dist, int relax,
+                    uint64_t *offsets, uint32_t *ids, uint64_t cap);
+
+/* number of objects in the READ buffer */
+int flk_num_objects(const flk_field *f, uint64_t *n);
+
+/* Field2D::get / get_location for every object (flockers/src/visualization/vis_state.rs:52, bird_vis.rs:23):
+ * copies the READ buffer, in (cell, id) order, to HOST arrays (any of them may be NULL). Synchronous. */
+int flk_snapshot(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n);
+
+/* the binning itself: cell_start[dw*dh+1] (flat cell = cx*dh+cy) and ids in sorted order */
+int flk_get_binning(flk_field *f, uint32_t *cell_start, uint32_t *sorted_ids);
+
+/* ---- timing / sync ----------------------------------------------------------------------------- */
+int flk_synchronize(flk_field *f);
+/* device time (CUDA events on the handle's stream) of the last flk_step / flk_lazy_update / flk_run call */
+int flk_elapsed_ms(flk_field *f, float *ms);
+/* the CUDA stream (cudaStream_t) all work of this handle is enqueued on */
+int flk_stream(flk_field *f, void **stream);
+/* kernels launched by this handle since creation */
+int flk_launch_count(const flk_field *f, uint64_t *n);
+/* average device time (ms) and launches of the step kernel since flk_profile_reset; CUDA events around each launch */
+int flk_profile_enable(flk_field *f, int on);
+/* flk_run replays a captured CUDA graph per tick (default on); off = plain launches */
+int flk_use_graph(flk_field *f, int on);
+int flk_profile_step_kernel(flk_field *f, double *total_ms, uint64_t *launches);
+
+/* pinned host memory helpers (fast flk_set_objects / flk_snapshot) */
+int flk_host_alloc(void **p, uint64_t bytes);
+int flk_host_free(void *p);
+
+const char *flk_last_error(void);
+const char *flk_version(void);
+
+/* ---- multi-GPU: one rank per GPU, x-strip decomposition (flockers_mpi) --------------------------- */
+
+/* NCCL unique id (128 bytes) created on rank 0 and distributed by the caller (e.g. torch.distributed) */
+int flk_dist_unique_id(uint8_t id128[128]);
+
+/* Kdtree::create_tree(...) (flockers_mpi/src/model/state.rs:33) replaced by a 1-D periodic strip
+ * decomposition over cell columns: rank r owns global columns [r*mx/world, (r+1)*mx/world).
+ * capacity is per rank.  The global field is width x height as in flk_field_create. */
+int flk_dist_create(float width, float height, float discretization, uint64_t capacity, int device,
+                    int rank, int world, const uint8_t id128[128], flk_field **out);
+
+/* get_block_by_location (flockers_mpi/src/model/state.rs:75, bird.rs:190): owner rank of a location */
+int flk_dist_owner(const flk_field *f, float x, float y, int32_t *rank);
+/* global cell-column range [col0,col1) owned by this rank */
+int flk_dist_strip(const flk_field *f, int32_t *col0, int32_t *col1);
+
+/* Distributed tick: before_step halo exchange + every owned Bird::step + after_step migration + update
+ * (flockers_mpi/src/model/state.rs:105-175).  flk_set_objects on a dist handle accepts only birds the
+ * rank owns (init scatter, state.rs:51-103, is done by the caller).  The first call performs the initial
+ * halo exchange.  flk_run on a dist handle loops this. */
+int flk_dist_step(flk_field *f, uint64_t step, uint64_t seed, const float *injected_r, uint64_t n_injected);
+
+/* number of birds this rank owns (ghosts excluded) — synchronising */
+int flk_dist_num_owned(flk_field *f, uint64_t *n);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLK_H */
