@@ -47,6 +47,7 @@ SIGNATURES = {
     "flk_profile_step_kernel": [_vp, _P(C.c_double), _P(_u64)],
     "flk_host_alloc": [_P(_vp), _u64],
     "flk_host_free": [_vp],
+    "flk_selftest_div2": [C.c_int, _u64, _u64, _P(_u64)],
     "flk_last_error": [],
     "flk_version": [],
     "flk_dist_unique_id": [_vp],

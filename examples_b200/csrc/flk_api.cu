@@ -507,6 +507,21 @@ int flk_use_graph(flk_field *f, int on) {
     return FLK_OK;
 }
 
+int flk_selftest_div2(int device, uint64_t n, uint64_t seed, uint64_t *mismatches) {
+    if (!mismatches || n == 0 || n > (1ull << 32)) return fail(FLK_E_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    unsigned long long *d = nullptr, h = 0;
+    CUDA_TRY(cudaMalloc(&d, 8));
+    CUDA_TRY(cudaMemset(d, 0, 8));
+    launch_selftest_div2(n, seed, d, 0);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(FLK_E_CUDA, "selftest: %s", cudaGetErrorString(e));
+    *mismatches = h;
+    return FLK_OK;
+}
+
 int flk_host_alloc(void **p, uint64_t bytes) {
     if (!p) return fail(FLK_E_INVALID, "p is null");
     CUDA_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault));

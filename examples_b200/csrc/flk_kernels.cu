@@ -48,29 +48,23 @@ __device__ __forceinline__ void for_each_window_run(const Geom &g, const uint32_
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_step
+// neighbour accumulation (bird.rs:44-71), candidates visited in query order
 // ------------------------------------------------------------------------------------------------
-template <bool RELAX, int MATH>
-__global__ void __launch_bounds__(128) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
-    const uint32_t lo = __ldg(s.cell_start + a.cell_lo);
-    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
-    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= hi) return;
-
-    const Rec me = s.rec[i];
-    const uint32_t my_id = s.ids[i];
-    const float W = g.W, H = g.H;
-    const float halfW = __fdiv_rn(W, 2.0f), halfH = __fdiv_rn(H, 2.0f);
-
-    // cell of this bird (same arithmetic as the binning that placed it)
-    const int gcx = cell_coord(me.x, g.d, g.mx + 1);
-    const int cy = cell_coord(me.y, g.d, g.dh);
-    const int lc = local_col(g, gcx);
-
-    float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;  // bird.rs:44-49
+struct Acc {
+    float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;   // bird.rs:44-49
     uint32_t nvec = 0;   // size of the query result (bird.rs:42 tests emptiness)
     int count = 0;       // bird.rs:50
+};
 
+template <bool RELAX, int MATH, bool SEAM>
+__device__ __forceinline__ void accumulate_window(const Geom &g, const Params &p, const Store &s, const Rec &me,
+                                                  uint32_t i, int lc, int cy, Acc &acc) {
+    const float W = g.W, H = g.H;
+    const float halfW = __fdiv_rn(W, 2.0f), halfH = __fdiv_rn(H, 2.0f);
+    float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
+    uint32_t nvec = 0;
+    int count = 0;
+    const float4 *__restrict__ rec = reinterpret_cast<const float4 *>(s.rec);
     for_each_window_run(g, s.cell_start, lc, cy, p.k, [&](uint32_t rs, uint32_t re) {
         uint32_t j = rs;
         while (true) {
@@ -78,9 +72,15 @@ __global__ void __launch_bounds__(128) k_step(const Geom g, const Params p, cons
             const uint32_t stop = (RELAX && i >= j && i < re) ? i : re;
 #pragma unroll 2
             for (; j < stop; ++j) {
-                const float4 o = __ldg(reinterpret_cast<const float4 *>(s.rec) + j);
-                const float dx = toroidal_distance(me.x, o.x, W, halfW);   // bird.rs:54
-                const float dy = toroidal_distance(me.y, o.y, H, halfH);   // bird.rs:55
+                const float4 o = __ldg(rec + j);
+                float dx, dy;
+                if (SEAM) {
+                    dx = toroidal_distance(me.x, o.x, W, halfW);   // bird.rs:54
+                    dy = toroidal_distance(me.y, o.y, H, halfH);   // bird.rs:55
+                } else {
+                    dx = __fadd_rn(me.x, -o.x);
+                    dy = __fadd_rn(me.y, -o.y);
+                }
                 const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));  // :59
                 if (!RELAX) {
                     // get_neighbors_within_distance keeps elem iff sqrt(dx^2+dy^2) <= dist
@@ -95,14 +95,17 @@ __global__ void __launch_bounds__(128) k_step(const Geom g, const Params p, cons
                     ++count;
                 }
                 const float den = __fadd_rn(__fmul_rn(sq, sq), 1.0f);
+                float qa, qb;
                 if (MATH == 0) {
-                    xa = __fadd_rn(xa, __fdiv_rn(dx, den));   // :60
-                    ya = __fadd_rn(ya, __fdiv_rn(dy, den));   // :61
+                    div2_rn(dx, dy, den, qa, qb);             // :60-61, two IEEE divisions
                 } else {
-                    const float inv = __frcp_rn(den);
-                    xa = __fadd_rn(xa, __fmul_rn(dx, inv));
-                    ya = __fadd_rn(ya, __fmul_rn(dy, inv));
+                    float inv;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+                    qa = __fmul_rn(dx, inv);
+                    qb = __fmul_rn(dy, inv);
                 }
+                xa = __fadd_rn(xa, qa);      // :60
+                ya = __fadd_rn(ya, qb);      // :61
                 xc = __fadd_rn(xc, dx);      // :64
                 yc = __fadd_rn(yc, dy);      // :65
                 xs = __fadd_rn(xs, o.z);     // :68
@@ -116,6 +119,39 @@ __global__ void __launch_bounds__(128) k_step(const Geom g, const Params p, cons
             count += (int)(re - rs) - ((i >= rs && i < re) ? 1 : 0);
         }
     });
+    acc.xa = xa; acc.ya = ya; acc.xc = xc; acc.yc = yc; acc.xs = xs; acc.ys = ys;
+    acc.nvec = nvec; acc.count = count;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_step
+// ------------------------------------------------------------------------------------------------
+template <bool RELAX, int MATH>
+__global__ void __launch_bounds__(128) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
+    const uint32_t lo = __ldg(s.cell_start + a.cell_lo);
+    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
+    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+
+    const Rec me = s.rec[i];
+    const uint32_t my_id = s.ids[i];
+    const float W = g.W, H = g.H;
+
+    // cell of this bird (same arithmetic as the binning that placed it)
+    const int gcx = cell_coord(me.x, g.d, g.mx + 1);
+    const int cy = cell_coord(me.y, g.d, g.dh);
+    const int lc = local_col(g, gcx);
+
+    Acc acc;
+    // Birds whose 3x3 window cannot touch the seam never take the |a-b| > dim/2 branch of toroidal_distance:
+    // cells are < 2d apart and dim >= 6d, so the plain difference is the toroidal one (exactly).
+    const bool interior = g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && gcx >= 1 && gcx <= g.mx - 2 &&
+                          cy >= 1 && cy <= g.my - 2;
+    if (interior) accumulate_window<RELAX, MATH, false>(g, p, s, me, i, lc, cy, acc);
+    else accumulate_window<RELAX, MATH, true>(g, p, s, me, i, lc, cy, acc);
+    float xa = acc.xa, ya = acc.ya, xc = acc.xc, yc = acc.yc, xs = acc.xs, ys = acc.ys;
+    const uint32_t nvec = acc.nvec;
+    const int count = acc.count;
 
     float avo_x = 0.0f, avo_y = 0.0f, coh_x = 0.0f, coh_y = 0.0f;   // bird.rs:36-40
     float rnd_x = 0.0f, rnd_y = 0.0f, con_x = 0.0f, con_y = 0.0f;
@@ -363,6 +399,43 @@ __global__ void __launch_bounds__(256) k_rank(const Store s, uint32_t ncell, int
 void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st) {
     const uint32_t nb = n_upper == 0 ? 1 : (n_upper + 255) / 256;
     k_rank<<<nb, 256, 0, st>>>(s, ncell, bump_step);
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics: div2_rn against __fdiv_rn on pseudo-random operands shaped like the hot loop's
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_selftest_div2(uint64_t n, uint64_t seed, unsigned long long *mismatches) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    uint32_t o0, o1;
+    philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 0x5e1f, 0, (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1);
+    uint32_t o2, o3;
+    philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 0x5e20, 0, (uint32_t)seed, (uint32_t)(seed >> 32), o2, o3);
+    // numerators: random sign/mantissa, exponent in [2^-70, 2^16] (covers the guard edge), some zeros/denormals
+    auto mk = [](uint32_t u, int emin, int span) {
+        const uint32_t e = (uint32_t)(127 + emin) + (u >> 23) % (uint32_t)span;
+        return __uint_as_float((u & 0x807fffffu) | (e << 23));
+    };
+    float a = mk(o0, -70, 87), b = mk(o1, -70, 87);
+    if ((o2 & 0xff) == 0) a = 0.0f;
+    if ((o2 & 0xff) == 1) b = __uint_as_float(o3 & 0x807fffffu);   // denormal
+    float d;
+    if (o2 & 0x100) {                       // d = sq*sq+1 from the numerators, as in bird.rs:59-61
+        const float sq = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+        d = __fadd_rn(__fmul_rn(sq, sq), 1.0f);
+    } else {
+        d = mk(o3, 0, 64);                  // [1, 2^64): crosses the 2^60 guard
+    }
+    float qa, qb;
+    div2_rn(a, b, d, qa, qb);
+    const float ra = __fdiv_rn(a, d), rb = __fdiv_rn(b, d);
+    const bool ok = (__float_as_uint(qa) == __float_as_uint(ra) || (qa != qa && ra != ra)) &&
+                    (__float_as_uint(qb) == __float_as_uint(rb) || (qb != qb && rb != rb));
+    if (!ok) atomicAdd(mismatches, 1ull);
+}
+
+void launch_selftest_div2(uint64_t n, uint64_t seed, unsigned long long *mismatches, cudaStream_t st) {
+    k_selftest_div2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, seed, mismatches);
 }
 
 __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *p, uint32_t v, uint64_t n) {

@@ -44,6 +44,7 @@ void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs 
 void launch_scan(const Store &s, uint32_t ncell_plus1, cudaStream_t st);
 void launch_scatter(const Store &s, uint32_t n_write_extent, cudaStream_t st);
 void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st);
+void launch_selftest_div2(uint64_t n, uint64_t seed, unsigned long long *mismatches, cudaStream_t st);
 void launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t st);
 void launch_split(const Store &s, uint32_t n, float2 *loc, float2 *ld, cudaStream_t st);
 void launch_query_count(const Geom &g, const Store &s, uint32_t nq, const float2 *loc, float dist, int relax,

@@ -136,6 +136,9 @@ int flk_profile_step_kernel(flk_field *f, double *total_ms, uint64_t *launches);
 int flk_host_alloc(void **p, uint64_t bytes);
 int flk_host_free(void *p);
 
+/* diagnostics: compares the kernels' shared-reciprocal IEEE division against __fdiv_rn on n operand pairs */
+int flk_selftest_div2(int device, uint64_t n, uint64_t seed, uint64_t *mismatches);
+
 const char *flk_last_error(void);
 const char *flk_version(void);
 
