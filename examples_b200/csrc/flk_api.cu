@@ -30,13 +30,16 @@ int field_alloc(flk_field *f) {
     const uint64_t cap = f->cap;
     const uint64_t m = (uint64_t)f->ncell + 1;
     Store &s = f->s;
+    s.cap = (uint32_t)cap;
+    if (f->g.mode != 1) s.capx = 0;
+    const uint64_t capw = cap + 2ull * s.capx;   // WRITE slots: stepped/uploaded + received from both neighbours
     CUDA_TRY(cudaMalloc(&s.rec, cap * sizeof(Rec)));
     CUDA_TRY(cudaMalloc(&s.ids, cap * 4));
     CUDA_TRY(cudaMalloc(&s.cell_start, m * 4));
-    CUDA_TRY(cudaMalloc(&s.trec, cap * sizeof(Rec)));
-    CUDA_TRY(cudaMalloc(&s.tid, cap * 4));
-    CUDA_TRY(cudaMalloc(&s.tkey, cap * 4));
-    CUDA_TRY(cudaMalloc(&s.tslot, cap * 4));
+    CUDA_TRY(cudaMalloc(&s.trec, capw * sizeof(Rec)));
+    CUDA_TRY(cudaMalloc(&s.tid, capw * 4));
+    CUDA_TRY(cudaMalloc(&s.tkey, capw * 4));
+    CUDA_TRY(cudaMalloc(&s.tslot, capw * 4));
     CUDA_TRY(cudaMalloc(&s.cnt, m * 4));
     // one scratch block: (sid, ssrc, skey) during lazy_update; upload / snapshot staging otherwise
     CUDA_TRY(cudaMalloc(&f->scratch, cap * 20 + 64));
@@ -47,6 +50,8 @@ int field_alloc(flk_field *f) {
     CUDA_TRY(cudaMalloc(&s.blocksum, nblk * 4));
     CUDA_TRY(cudaMalloc(&s.step_dev, 8));
     CUDA_TRY(cudaMalloc(&s.n_read_dev, 4));
+    CUDA_TRY(cudaMalloc(&s.err_flag, 4));
+    CUDA_TRY(cudaMemsetAsync(s.err_flag, 0, 4, f->stream));
     CUDA_TRY(cudaMemsetAsync(s.cell_start, 0, m * 4, f->stream));
     CUDA_TRY(cudaMemsetAsync(s.cnt, 0, m * 4, f->stream));
     CUDA_TRY(cudaMemsetAsync(s.step_dev, 0, 8, f->stream));
@@ -58,7 +63,7 @@ void field_free(flk_field *f) {
     Store &s = f->s;
     cudaFree(s.rec); cudaFree(s.ids); cudaFree(s.cell_start); cudaFree(s.trec); cudaFree(s.tid);
     cudaFree(s.tkey); cudaFree(s.tslot); cudaFree(s.cnt); cudaFree(f->scratch); cudaFree(s.blocksum);
-    cudaFree(s.step_dev); cudaFree(s.n_read_dev);
+    cudaFree(s.step_dev); cudaFree(s.n_read_dev); cudaFree(s.err_flag);
     if (f->d_injected) cudaFree(f->d_injected);
     if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
     for (auto &e : f->prof_events) cudaEventDestroy(e);
@@ -114,7 +119,7 @@ int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc,
     CUDA_TRY(cudaMemcpyAsync(d_id, id, n * 4, cudaMemcpyHostToDevice, f->stream));
     CUDA_TRY(cudaMemcpyAsync(d_loc, loc, n * 8, cudaMemcpyHostToDevice, f->stream));
     CUDA_TRY(cudaMemcpyAsync(d_ld, ld, n * 8, cudaMemcpyHostToDevice, f->stream));
-    launch_ingest(f->g, f->s, (uint32_t)n, d_id, d_loc, d_ld, (uint32_t)f->w_count, f->stream);
+    launch_ingest(f->g, f->s, (uint32_t)n, d_id, d_loc, d_ld, (uint32_t)f->w_count, 1, f->stream);
     f->launches += 1;
     CUDA_TRY(cudaGetLastError());
     f->w_count += n;
@@ -125,7 +130,7 @@ int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc,
 int enqueue_lazy_update(flk_field *f, int bump_step) {
     const uint32_t m = f->ncell + 1;
     launch_scan(f->s, m, f->stream);
-    launch_scatter(f->s, (uint32_t)f->w_count, f->stream);
+    launch_scatter(f->s, (uint32_t)f->w_count, f->g.mode == 1, f->stream);
     launch_rank(f->s, (uint32_t)f->w_count, f->ncell, bump_step, f->stream);
     f->launches += 3 + (f->w_count ? 1 : 0) + 1;
     CUDA_TRY(cudaGetLastError());
@@ -144,6 +149,7 @@ int enqueue_step(flk_field *f, uint64_t step, int use_step_dev, uint64_t seed, c
     a.injected = d_inj; a.n_injected = n_inj;
     a.out_base = (uint32_t)f->w_count;
     a.math_mode = f->math_mode;
+    a.identity = 0;
     const bool prof = f->profile && !f->capturing;
     if (prof) {
         cudaEvent_t e0, e1;

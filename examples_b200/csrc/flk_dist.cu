@@ -1,19 +1,552 @@
-// flk_dist.cu — multi-GPU strip decomposition (flockers_mpi protocol).  Placeholder until the NCCL path lands.
+// flk_dist.cu — multi-GPU Flockers: 1-D periodic strip decomposition over cell columns, one strip per GPU.
+//
+// Follows the flockers_mpi protocol (flockers_mpi/src/model/state.rs:105-175, bird.rs:185-195):
+//   before_step  ghosts of the neighbouring strips are present in the READ buffer          (halo)
+//   step         every OWNED bird steps; its successor is routed by the owner of its new location
+//   after_step   leavers go to their new owner, arrivals are inserted                       (migration)
+//   update       lazy_update
+// JUMP (0.7) < discretisation, so a bird crosses at most one column per tick: both the migrants and next
+// tick's ghosts of a neighbour are exactly "successors that landed in one of the two columns next to the
+// shared boundary".  One message per neighbour per tick therefore carries halo AND migration.
+//
+// Two transports move the fixed-capacity messages:
+//   NCCL   one process per GPU (torchrun); ncclSend/ncclRecv grouped on the handle's stream.  libnccl is
+//          dlopen'ed so that single-GPU users need no NCCL at all.
+//   LOCAL  all strips driven by one host thread (flk_mgpu_*): cudaMemcpyPeerAsync between the handles'
+//          buffers, ordered with events.  Also how the strip logic is tested on a single GPU.
+#include <dlfcn.h>
+
+#include <cstring>
+
 #include "../../include/flk.h"
 #include "flk_internal.cuh"
 
+using namespace flk;
+
+// ---- minimal NCCL surface (ABI-stable subset of nccl.h; the library is resolved at run time) ----------------
+extern "C" {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+}
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclUint8 = 1;  // ncclUint8
+
+int nccl_load() {
+    if (g_nccl.lib) return FLK_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(FLK_E_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                   \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                            \
+    if (!g_nccl.field) return fail(FLK_E_NCCL, "libnccl lacks %s", name)
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.lib = h;
+    return FLK_OK;
+}
+#define NCCL_TRY(x)                                                                                      \
+    do {                                                                                                 \
+        ncclResult_t r_ = (x);                                                                           \
+        if (r_ != 0) return fail(FLK_E_NCCL, "%s: %s", #x, g_nccl.GetErrorString(r_));                   \
+    } while (0)
+}  // namespace
+
+struct flk_dist_state {
+    int rank = 0, world = 1;
+    int transport = 0;  // 0 NCCL, 1 LOCAL
+    ncclComm_t comm = nullptr;
+    int left = 0, right = 0;
+    uint8_t *xbuf = nullptr;           // sendL | sendR | recvL | recvR
+    flk_field **group = nullptr;       // LOCAL: all handles of the group (owned by rank 0's state)
+    cudaEvent_t ev_sent = nullptr;     // my send buffers are complete
+    cudaEvent_t ev_copied = nullptr;   // I have copied my neighbours' send buffers
+    bool copied_valid = false;
+    bool committed = false;
+};
+
 namespace flk {
-void dist_free(flk_field *) {}
-int dist_set_objects(flk_field *, uint64_t, const uint32_t *, const float *, const float *) { return fail(FLK_E_UNSUPPORTED, "dist not built"); }
-int dist_run(flk_field *, uint64_t, uint64_t, uint64_t) { return fail(FLK_E_UNSUPPORTED, "dist not built"); }
-int dist_refresh_counts(flk_field *) { return fail(FLK_E_UNSUPPORTED, "dist not built"); }
+
+void dist_free(flk_field *f) {
+    flk_dist_state *d = f->dist;
+    if (!d) return;
+    if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+    if (d->xbuf) cudaFree(d->xbuf);
+    if (d->ev_sent) cudaEventDestroy(d->ev_sent);
+    if (d->ev_copied) cudaEventDestroy(d->ev_copied);
+    if (d->rank == 0 && d->group) delete[] d->group;
+    delete d;
+    f->dist = nullptr;
+}
+
+static void strip_of(int mx, int world, int rank, int *c0, int *c1) {
+    *c0 = (int)((long long)rank * mx / world);
+    *c1 = (int)((long long)(rank + 1) * mx / world);
+}
+
+// common part of flk_dist_create / flk_mgpu_create
+static int dist_field_new(float w, float h, float disc, uint64_t capacity, int device, int rank, int world,
+                          int transport, flk_field **out) {
+    *out = nullptr;
+    if (world < 2) return fail(FLK_E_INVALID, "strip decomposition needs world >= 2 (use flk_field_create for one GPU)");
+    if (rank < 0 || rank >= world) return fail(FLK_E_INVALID, "rank %d out of range", rank);
+    if (capacity == 0 || capacity > 0x7fffffffull) return fail(FLK_E_INVALID, "capacity must be in [1, 2^31)");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(FLK_E_CUDA, "no CUDA device (%s): libflk has no CPU fallback", cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(FLK_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    flk_field *f = new flk_field();
+    f->device = device;
+    int rc = setup_geometry(f, w, h, disc, 1);
+    if (rc) { delete f; return rc; }
+    Geom &g = f->g;
+    if (g.mx < 2 * world) {
+        delete f;
+        return fail(FLK_E_UNSUPPORTED, "%d cell columns cannot be split into %d strips of >= 2 columns", g.mx, world);
+    }
+    int c0, c1;
+    strip_of(g.mx, world, rank, &c0, &c1);
+    g.mode = 1; g.col0 = c0; g.nown = c1 - c0; g.has_slack = (c0 == 0);
+    g.ncols = g.nown + 3;
+    f->p = Params{0.8f, 1.0f, 1.1f, 0.7f, 1.0f, 0.7f, 10.0f, 1, 1};
+    rc = update_window(f);
+    if (rc) { delete f; return rc; }
+    f->cap = capacity;
+    f->ncell = (uint32_t)g.ncols * (uint32_t)g.dh;
+    // exchange capacity: the two boundary columns hold ~2/nown of the strip; allow 8x that (clustered flocks)
+    uint64_t capx = 8 * (capacity / (uint64_t)g.nown) + 4096;
+    if (capx > capacity) capx = capacity;
+    f->s.capx = (uint32_t)capx;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&f->ev0));
+    CUDA_TRY(cudaEventCreate(&f->ev1));
+    rc = field_alloc(f);
+    if (rc) { field_free(f); delete f; return rc; }
+    flk_dist_state *d = new flk_dist_state();
+    f->dist = d;
+    d->rank = rank; d->world = world; d->transport = transport;
+    d->left = (rank + world - 1) % world;
+    d->right = (rank + 1) % world;
+    const size_t xb = (xbuf_bytes(f->s.capx) + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&d->xbuf, 4 * xb);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d->xbuf, 0, 4 * xb, f->stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_sent, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        dist_free(f); field_free(f); delete f;
+        return fail(FLK_E_CUDA, "dist alloc: %s", cudaGetErrorString(e));
+    }
+    f->s.sendL = d->xbuf; f->s.sendR = d->xbuf + xb; f->s.recvL = d->xbuf + 2 * xb; f->s.recvR = d->xbuf + 3 * xb;
+    f->n_read = 0;
+    *out = f;
+    return FLK_OK;
+}
+
+// phase 1 of a tick on one strip: clear the outgoing messages, step (or re-stage) every owned bird
+static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const float2 *d_inj, uint32_t n_inj, int identity) {
+    flk_dist_state *d = f->dist;
+    if (d->transport == 1 && d->copied_valid) {
+        // my neighbours read my send buffers last tick: wait until their copies are done
+        flk_field **grp = d->group;
+        CUDA_TRY(cudaStreamWaitEvent(f->stream, grp[d->left]->dist->ev_copied, 0));
+        CUDA_TRY(cudaStreamWaitEvent(f->stream, grp[d->right]->dist->ev_copied, 0));
+    }
+    CUDA_TRY(cudaMemsetAsync(f->s.sendL, 0, sizeof(XHdr), f->stream));
+    CUDA_TRY(cudaMemsetAsync(f->s.sendR, 0, sizeof(XHdr), f->stream));
+    StepArgs a;
+    a.cell_lo = 0; a.cell_hi = f->ncell;
+    a.step = step; a.use_step_dev = 0; a.seed = seed;
+    a.injected = d_inj; a.n_injected = n_inj;
+    a.out_base = 0;
+    a.math_mode = f->math_mode;
+    a.identity = identity;
+    const bool prof = f->profile && !identity;
+    if (prof) {
+        cudaEvent_t e0, e1;
+        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+        f->prof_events.push_back(e0); f->prof_events.push_back(e1);
+        CUDA_TRY(cudaEventRecord(e0, f->stream));
+    }
+    launch_step(f->g, f->p, f->s, a, (uint32_t)f->cap, f->stream);
+    if (prof) CUDA_TRY(cudaEventRecord(f->prof_events.back(), f->stream));
+    f->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    if (d->transport == 1) CUDA_TRY(cudaEventRecord(d->ev_sent, f->stream));
+    return FLK_OK;
+}
+
+// phase 2: move the messages
+static int dist_phase_exchange(flk_field *f) {
+    flk_dist_state *d = f->dist;
+    const size_t nbytes = xbuf_bytes(f->s.capx);
+    if (d->transport == 0) {
+        NCCL_TRY(g_nccl.GroupStart());
+        NCCL_TRY(g_nccl.Send(f->s.sendL, nbytes, kNcclUint8, d->left, d->comm, f->stream));
+        NCCL_TRY(g_nccl.Send(f->s.sendR, nbytes, kNcclUint8, d->right, d->comm, f->stream));
+        // order matters only for world==2 (both messages come from the same peer): its sendL is my recvR
+        NCCL_TRY(g_nccl.Recv(f->s.recvR, nbytes, kNcclUint8, d->right, d->comm, f->stream));
+        NCCL_TRY(g_nccl.Recv(f->s.recvL, nbytes, kNcclUint8, d->left, d->comm, f->stream));
+        NCCL_TRY(g_nccl.GroupEnd());
+    } else {
+        flk_field *L = d->group[d->left], *R = d->group[d->right];
+        CUDA_TRY(cudaStreamWaitEvent(f->stream, L->dist->ev_sent, 0));
+        CUDA_TRY(cudaStreamWaitEvent(f->stream, R->dist->ev_sent, 0));
+        CUDA_TRY(cudaMemcpyPeerAsync(f->s.recvL, f->device, L->s.sendR, L->device, nbytes, f->stream));
+        CUDA_TRY(cudaMemcpyPeerAsync(f->s.recvR, f->device, R->s.sendL, R->device, nbytes, f->stream));
+        CUDA_TRY(cudaEventRecord(d->ev_copied, f->stream));
+        d->copied_valid = true;
+    }
+    return FLK_OK;
+}
+
+// phase 3: arrivals join the WRITE buffer, then lazy_update
+static int dist_phase_finish(flk_field *f) {
+    launch_unpack(f->g, f->s, f->stream);
+    f->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    f->w_count = f->cap;  // grid bound only; validity is decided on the device
+    int rc = enqueue_lazy_update(f, 0);
+    f->n_read = f->cap;   // upper bound (exact count lives on the device)
+    f->w_count = 0;
+    return rc;
+}
+
+static int dist_tick(flk_field *f, uint64_t step, uint64_t seed, const float2 *d_inj, uint32_t n_inj, int identity) {
+    int rc = dist_phase_step(f, step, seed, d_inj, n_inj, identity);
+    if (!rc) rc = dist_phase_exchange(f);
+    if (!rc) rc = dist_phase_finish(f);
+    return rc;
+}
+
+// lazy_update of the birds uploaded so far (owned only), before the first halo exchange
+static int dist_publish_uploads(flk_field *f) {
+    const uint64_t w = f->w_count;
+    launch_scan(f->s, f->ncell + 1, f->stream);
+    if (w) {
+        // uploads sit at WRITE [0,w): plain (non-dist) scatter
+        launch_scatter(f->s, (uint32_t)w, 0, f->stream);
+    }
+    launch_rank(f->s, (uint32_t)w, f->ncell, 0, f->stream);
+    f->launches += 4 + (w ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    f->n_read = w;
+    f->w_count = 0;
+    return FLK_OK;
+}
+
+int dist_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld) {
+    f->dist->committed = false;
+    return write_append(f, n, id, loc, ld);
+}
+
+static int dist_check_errors(flk_field *f) {
+    uint32_t flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, f->s.err_flag, 4, cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    if (flag & ERR_CAPACITY) return fail(FLK_E_CAPACITY, "rank %d holds more birds than its capacity %llu", f->dist->rank, (unsigned long long)f->cap);
+    if (flag & ERR_EXCHANGE) return fail(FLK_E_CAPACITY, "rank %d: halo/migration message exceeded %u birds", f->dist->rank, f->s.capx);
+    return FLK_OK;
+}
+
+int dist_refresh_counts(flk_field *f) {
+    int rc = dist_check_errors(f);
+    if (rc) return rc;
+    uint32_t n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, f->s.n_read_dev, 4, cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    f->n_read = n;
+    return FLK_OK;
+}
+
+int dist_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed) {
+    flk_dist_state *d = f->dist;
+    if (d->transport != 0) return fail(FLK_E_STATE, "use flk_mgpu_run on an in-process group");
+    if (!d->committed) return fail(FLK_E_STATE, "call flk_dist_commit after uploading birds");
+    CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+    for (uint64_t t = 0; t < n_steps; ++t) {
+        int rc = dist_tick(f, first_step + t, seed, nullptr, 0, 0);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+    return FLK_OK;
+}
+
 }  // namespace flk
 
 extern "C" {
-int flk_dist_unique_id(uint8_t *) { return flk::fail(FLK_E_UNSUPPORTED, "dist not built"); }
-int flk_dist_create(float, float, float, uint64_t, int, int, int, const uint8_t *, flk_field **) { return flk::fail(FLK_E_UNSUPPORTED, "dist not built"); }
-int flk_dist_owner(const flk_field *, float, float, int32_t *) { return flk::fail(FLK_E_UNSUPPORTED, "dist not built"); }
-int flk_dist_strip(const flk_field *, int32_t *, int32_t *) { return flk::fail(FLK_E_UNSUPPORTED, "dist not built"); }
-int flk_dist_step(flk_field *, uint64_t, uint64_t, const float *, uint64_t) { return flk::fail(FLK_E_UNSUPPORTED, "dist not built"); }
-int flk_dist_num_owned(flk_field *, uint64_t *) { return flk::fail(FLK_E_UNSUPPORTED, "dist not built"); }
+
+int flk_dist_unique_id(uint8_t *id128) {
+    if (!id128) return fail(FLK_E_INVALID, "id128 is null");
+    int rc = nccl_load();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return FLK_OK;
 }
+
+int flk_dist_create(float width, float height, float discretization, uint64_t capacity, int device, int rank, int world,
+                    const uint8_t *id128, flk_field **out) {
+    if (!out || !id128) return fail(FLK_E_INVALID, "null argument");
+    int rc = nccl_load();
+    if (rc) return rc;
+    rc = dist_field_new(width, height, discretization, capacity, device, rank, world, 0, out);
+    if (rc) return rc;
+    ncclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&(*out)->dist->comm, world, id, rank);
+    if (r != 0) {
+        int code = fail(FLK_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+        flk_field_destroy(*out);
+        *out = nullptr;
+        return code;
+    }
+    return FLK_OK;
+}
+
+int flk_mgpu_create(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
+                    const int *devices, flk_field **out) {
+    if (!out || !devices || n < 2) return fail(FLK_E_INVALID, "need n >= 2 devices");
+    flk_field **grp = new flk_field *[n];
+    for (int r = 0; r < n; ++r) {
+        int rc = dist_field_new(width, height, discretization, capacity_per_rank, devices[r], r, n, 1, &grp[r]);
+        if (rc) {
+            for (int q = 0; q < r; ++q) { grp[q]->dist->group = nullptr; flk_field_destroy(grp[q]); }
+            delete[] grp;
+            return rc;
+        }
+    }
+    for (int r = 0; r < n; ++r) {
+        grp[r]->dist->group = grp;
+        out[r] = grp[r];
+        // direct peer copies over NVLink where the topology allows it
+        for (int q = 0; q < n; ++q) {
+            if (devices[q] == devices[r]) continue;
+            int can = 0;
+            cudaSetDevice(devices[r]);
+            if (cudaDeviceCanAccessPeer(&can, devices[r], devices[q]) == cudaSuccess && can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[q], 0);
+                if (e != cudaSuccess) cudaGetLastError();  // already enabled
+            }
+        }
+    }
+    return FLK_OK;
+}
+
+int flk_dist_strip(const flk_field *f, int32_t *col0, int32_t *col1) {
+    if (!f) return fail(FLK_E_INVALID, "null handle");
+    if (col0) *col0 = f->g.mode == 1 ? f->g.col0 : 0;
+    if (col1) *col1 = f->g.mode == 1 ? f->g.col0 + f->g.nown : f->g.mx;
+    return FLK_OK;
+}
+
+int flk_dist_owner(const flk_field *f, float x, float y, int32_t *rank) {
+    (void)y;
+    if (!f || !rank) return fail(FLK_E_INVALID, "null argument");
+    if (f->g.mode != 1) { *rank = 0; return FLK_OK; }
+    float q = std::floor(x / f->g.d);   // same f32 arithmetic as the device binning
+    int gc = (q != q) ? 0 : (q >= 2147483648.0f ? 0x7fffffff : (q <= -2147483648.0f ? -0x7fffffff - 1 : (int)q));
+    if (gc < 0) gc = 0;
+    if (gc >= f->g.mx) { *rank = 0; return FLK_OK; }   // the slack column belongs to the strip holding column 0
+    const int world = f->dist->world;
+    for (int r = 0; r < world; ++r) {
+        int c0, c1;
+        strip_of(f->g.mx, world, r, &c0, &c1);
+        if (gc >= c0 && gc < c1) { *rank = r; return FLK_OK; }
+    }
+    return fail(FLK_E_INVALID, "no owner for column %d", gc);
+}
+
+// publish the uploaded birds and build the first halo (state.rs:113-133)
+int flk_dist_commit(flk_field *f) {
+    CHECK_HANDLE(f);
+    if (f->g.mode != 1) return flk_lazy_update(f);
+    if (f->dist->transport != 0) return fail(FLK_E_STATE, "use flk_mgpu_commit on an in-process group");
+    int rc = flush_pending(f);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+    rc = dist_publish_uploads(f);
+    if (!rc) rc = dist_tick(f, 0, 0, nullptr, 0, 1);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+    f->dist->committed = true;
+    return FLK_OK;
+}
+
+int flk_dist_step(flk_field *f, uint64_t step, uint64_t seed, const float *injected_r, uint64_t n_injected) {
+    CHECK_HANDLE(f);
+    if (f->g.mode != 1) {
+        int rc = flk_step(f, step, seed, injected_r, n_injected);
+        return rc ? rc : flk_lazy_update(f);
+    }
+    if (f->dist->transport != 0) return fail(FLK_E_STATE, "use flk_mgpu_step on an in-process group");
+    if (!f->dist->committed) return fail(FLK_E_STATE, "call flk_dist_commit after uploading birds");
+    const float2 *d_inj = nullptr;
+    if (injected_r) {
+        int rc = upload_injected(f, injected_r, n_injected);
+        if (rc) return rc;
+        d_inj = f->d_injected;
+    }
+    CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+    int rc = dist_tick(f, step, seed, d_inj, (uint32_t)n_injected, 0);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+    return FLK_OK;
+}
+
+static int mgpu_check(flk_field **hs, int n) {
+    if (!hs || n < 2) return fail(FLK_E_INVALID, "bad group");
+    for (int r = 0; r < n; ++r)
+        if (!hs[r] || !hs[r]->dist || hs[r]->dist->transport != 1 || hs[r]->dist->world != n || hs[r]->dist->rank != r)
+            return fail(FLK_E_INVALID, "handle %d is not rank %d of an in-process group of %d", r, r, n);
+    return FLK_OK;
+}
+
+static int mgpu_tick(flk_field **hs, int n, uint64_t step, uint64_t seed, const float *injected_r, uint64_t n_injected,
+                     int identity) {
+    for (int r = 0; r < n; ++r) {
+        flk_field *f = hs[r];
+        CUDA_TRY(cudaSetDevice(f->device));
+        const float2 *d_inj = nullptr;
+        if (injected_r) {
+            int rc = upload_injected(f, injected_r, n_injected);
+            if (rc) return rc;
+            d_inj = f->d_injected;
+        }
+        int rc = dist_phase_step(f, step, seed, d_inj, (uint32_t)n_injected, identity);
+        if (rc) return rc;
+    }
+    for (int r = 0; r < n; ++r) {
+        CUDA_TRY(cudaSetDevice(hs[r]->device));
+        int rc = dist_phase_exchange(hs[r]);
+        if (rc) return rc;
+    }
+    for (int r = 0; r < n; ++r) {
+        CUDA_TRY(cudaSetDevice(hs[r]->device));
+        int rc = dist_phase_finish(hs[r]);
+        if (rc) return rc;
+    }
+    return FLK_OK;
+}
+
+int flk_mgpu_commit(flk_field **hs, int n) {
+    int rc = mgpu_check(hs, n);
+    if (rc) return rc;
+    for (int r = 0; r < n; ++r) {
+        CUDA_TRY(cudaSetDevice(hs[r]->device));
+        rc = flush_pending(hs[r]);
+        if (!rc) rc = dist_publish_uploads(hs[r]);
+        if (rc) return rc;
+    }
+    rc = mgpu_tick(hs, n, 0, 0, nullptr, 0, 1);
+    if (rc) return rc;
+    for (int r = 0; r < n; ++r) hs[r]->dist->committed = true;
+    return FLK_OK;
+}
+
+int flk_mgpu_step(flk_field **hs, int n, uint64_t step, uint64_t seed, const float *injected_r, uint64_t n_injected) {
+    int rc = mgpu_check(hs, n);
+    if (rc) return rc;
+    for (int r = 0; r < n; ++r)
+        if (!hs[r]->dist->committed) return fail(FLK_E_STATE, "call flk_mgpu_commit after uploading birds");
+    return mgpu_tick(hs, n, step, seed, injected_r, n_injected, 0);
+}
+
+int flk_mgpu_run(flk_field **hs, int n, uint64_t first_step, uint64_t n_steps, uint64_t seed) {
+    int rc = mgpu_check(hs, n);
+    if (rc) return rc;
+    for (int r = 0; r < n; ++r) {
+        if (!hs[r]->dist->committed) return fail(FLK_E_STATE, "call flk_mgpu_commit after uploading birds");
+        CUDA_TRY(cudaSetDevice(hs[r]->device));
+        CUDA_TRY(cudaEventRecord(hs[r]->ev0, hs[r]->stream));
+    }
+    for (uint64_t t = 0; t < n_steps; ++t) {
+        rc = mgpu_tick(hs, n, first_step + t, seed, nullptr, 0, 0);
+        if (rc) return rc;
+    }
+    for (int r = 0; r < n; ++r) {
+        CUDA_TRY(cudaSetDevice(hs[r]->device));
+        CUDA_TRY(cudaEventRecord(hs[r]->ev1, hs[r]->stream));
+    }
+    return FLK_OK;
+}
+
+int flk_dist_num_owned(flk_field *f, uint64_t *n) {
+    CHECK_HANDLE(f);
+    if (!n) return fail(FLK_E_INVALID, "n is null");
+    if (f->g.mode != 1) { *n = f->n_read; return FLK_OK; }
+    int rc = dist_check_errors(f);
+    if (rc) return rc;
+    // owned birds = cells of local columns [1, nown] plus the slack column
+    uint32_t b[4];
+    const uint32_t dh = (uint32_t)f->g.dh, nown = (uint32_t)f->g.nown;
+    const uint32_t idx[4] = {1 * dh, (nown + 1) * dh, (nown + 2) * dh, (nown + 3) * dh};
+    for (int i = 0; i < 4; ++i)
+        CUDA_TRY(cudaMemcpyAsync(&b[i], f->s.cell_start + idx[i], 4, cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    *n = (uint64_t)(b[1] - b[0]) + (b[3] - b[2]);
+    return FLK_OK;
+}
+
+// snapshot of the birds this rank OWNS (ghost copies excluded), (cell, id) order
+int flk_dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n) {
+    CHECK_HANDLE(f);
+    if (f->g.mode != 1) return flk_snapshot(f, id, loc, last_d, n);
+    int rc = dist_check_errors(f);
+    if (rc) return rc;
+    uint32_t b[4];
+    const uint32_t dh = (uint32_t)f->g.dh, nown = (uint32_t)f->g.nown;
+    const uint32_t idx[4] = {1 * dh, (nown + 1) * dh, (nown + 2) * dh, (nown + 3) * dh};
+    for (int i = 0; i < 4; ++i)
+        CUDA_TRY(cudaMemcpyAsync(&b[i], f->s.cell_start + idx[i], 4, cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    const uint64_t n0 = b[1] - b[0], n1 = b[3] - b[2];
+    const uint64_t tot = (uint64_t)b[3];
+    if (n) *n = n0 + n1;
+    if (tot && (loc || last_d)) {
+        float2 *d_loc = reinterpret_cast<float2 *>(f->scratch);
+        float2 *d_ld = d_loc + tot;
+        launch_split(f->s, (uint32_t)tot, d_loc, d_ld, f->stream);
+        f->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        const uint64_t off[2] = {b[0], b[2]}, len[2] = {n0, n1}, dst[2] = {0, n0};
+        for (int k = 0; k < 2; ++k) {
+            if (!len[k]) continue;
+            if (loc) CUDA_TRY(cudaMemcpyAsync(loc + 2 * dst[k], d_loc + off[k], len[k] * 8, cudaMemcpyDeviceToHost, f->stream));
+            if (last_d) CUDA_TRY(cudaMemcpyAsync(last_d + 2 * dst[k], d_ld + off[k], len[k] * 8, cudaMemcpyDeviceToHost, f->stream));
+        }
+    }
+    if (id) {
+        if (n0) CUDA_TRY(cudaMemcpyAsync(id, f->s.ids + b[0], n0 * 4, cudaMemcpyDeviceToHost, f->stream));
+        if (n1) CUDA_TRY(cudaMemcpyAsync(id + n0, f->s.ids + b[2], n1 * 4, cudaMemcpyDeviceToHost, f->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    return FLK_OK;
+}
+
+}  // extern "C"

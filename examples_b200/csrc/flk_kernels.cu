@@ -9,6 +9,8 @@
 //   k_query_*   Field2D::get_neighbors_within_{relax_,}distance (bird.rs:29-31)
 //
 // No tensor cores: the path has no dense contraction.
+#include <cstdlib>
+
 #include "flk_kernels.cuh"
 
 namespace flk {
@@ -56,21 +58,24 @@ struct Acc {
     int count = 0;       // bird.rs:50
 };
 
-template <bool RELAX, int MATH, bool SEAM>
-__device__ __forceinline__ void accumulate_window(const Geom &g, const Params &p, const Store &s, const Rec &me,
+// MATH: 0 = exact, guarded per pair; 1 = fast (approximate reciprocal); 2 = exact, branch-free with a sticky
+// "recompute me" flag (returned)
+template <bool RELAX, int MATH, bool SEAM, int UNROLL>
+__device__ __forceinline__ bool accumulate_window(const Geom &g, const Params &p, const Store &s, const Rec &me,
                                                   uint32_t i, int lc, int cy, Acc &acc) {
     const float W = g.W, H = g.H;
     const float halfW = __fdiv_rn(W, 2.0f), halfH = __fdiv_rn(H, 2.0f);
     float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
     uint32_t nvec = 0;
     int count = 0;
+    float min_num = __int_as_float(0x7f800000);
     const float4 *__restrict__ rec = reinterpret_cast<const float4 *>(s.rec);
     for_each_window_run(g, s.cell_start, lc, cy, p.k, [&](uint32_t rs, uint32_t re) {
         uint32_t j = rs;
         while (true) {
             // the caller itself is part of the query result and skipped by id (bird.rs:53): split the run at i
             const uint32_t stop = (RELAX && i >= j && i < re) ? i : re;
-#pragma unroll 2
+#pragma unroll UNROLL
             for (; j < stop; ++j) {
                 const float4 o = __ldg(rec + j);
                 float dx, dy;
@@ -98,6 +103,8 @@ __device__ __forceinline__ void accumulate_window(const Geom &g, const Params &p
                 float qa, qb;
                 if (MATH == 0) {
                     div2_rn(dx, dy, den, qa, qb);             // :60-61, two IEEE divisions
+                } else if (MATH == 2) {
+                    div2_rn_sticky(dx, dy, den, qa, qb, min_num);
                 } else {
                     float inv;
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
@@ -121,13 +128,49 @@ __device__ __forceinline__ void accumulate_window(const Geom &g, const Params &p
     });
     acc.xa = xa; acc.ya = ya; acc.xc = xc; acc.yc = yc; acc.xs = xs; acc.ys = ys;
     acc.nvec = nvec; acc.count = count;
+    return !(min_num >= 0x1p-60f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Field2D::set_object_location(*self, loc) (bird.rs:142-144): WRITE entry w + per-cell arrival slot.
+// Strip mode adds the flockers_mpi routing (bird.rs:190-195, state.rs:113-175): a successor landing in one of
+// the two columns next to a strip boundary is also appended to the message for that neighbour (it is either a
+// migrant or next tick's ghost there); one landing outside the local columns is not kept here.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void xbuf_append(const Store &s, uint8_t *buf, const Rec &r, uint32_t id) {
+    const uint32_t slot = atomicAdd(&reinterpret_cast<XHdr *>(buf)->count, 1u);
+    if (slot < s.capx) {
+        reinterpret_cast<float4 *>(xbuf_rec(buf))[slot] = make_float4(r.x, r.y, r.ldx, r.ldy);
+        xbuf_id(buf, s.capx)[slot] = id;
+    } else {
+        atomicOr(s.err_flag, ERR_EXCHANGE);
+    }
+}
+
+__device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, const Rec &out, uint32_t id, uint32_t w) {
+    const int ncx = cell_coord(out.x, g.d, g.mx + 1);
+    const int ncy = cell_coord(out.y, g.d, g.dh);
+    const int nlc = local_col(g, ncx);
+    uint32_t key = KEY_INVALID, slot = 0;
+    if (nlc != FLK_DROP) {
+        key = (uint32_t)nlc * (uint32_t)g.dh + (uint32_t)ncy;
+        slot = atomicAdd(s.cnt + key, 1u);
+    }
+    reinterpret_cast<float4 *>(s.trec)[w] = make_float4(out.x, out.y, out.ldx, out.ldy);
+    s.tid[w] = id;
+    s.tkey[w] = key;
+    s.tslot[w] = slot;
+    if (g.mode == 1) {
+        if (nlc == 0 || nlc == 1) xbuf_append(s, s.sendL, out, id);
+        if (nlc == g.nown || nlc == g.nown + 1 || (nlc == FLK_DROP && ncx >= g.mx)) xbuf_append(s, s.sendR, out, id);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 // k_step
 // ------------------------------------------------------------------------------------------------
-template <bool RELAX, int MATH>
-__global__ void __launch_bounds__(128) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
+template <bool RELAX, int MATH, int VARIANT>
+__global__ void __launch_bounds__(256, (VARIANT == 3 ? 5 : 4)) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
     const uint32_t lo = __ldg(s.cell_start + a.cell_lo);
     const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
     const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
@@ -141,14 +184,34 @@ __global__ void __launch_bounds__(128) k_step(const Geom g, const Params p, cons
     const int gcx = cell_coord(me.x, g.d, g.mx + 1);
     const int cy = cell_coord(me.y, g.d, g.dh);
     const int lc = local_col(g, gcx);
+    const uint32_t w = a.out_base + i;
+    if (g.mode == 1 && (lc == 0 || lc == g.nown + 1)) {
+        // ghost copy (flockers_mpi: received_neighbors): stepped by its owner, dropped here
+        s.tkey[w] = KEY_INVALID;
+        return;
+    }
+    if (a.identity) {
+        emit_successor(g, s, me, my_id, w);
+        return;
+    }
 
     Acc acc;
     // Birds whose 3x3 window cannot touch the seam never take the |a-b| > dim/2 branch of toroidal_distance:
     // cells are < 2d apart and dim >= 6d, so the plain difference is the toroidal one (exactly).
     const bool interior = g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && gcx >= 1 && gcx <= g.mx - 2 &&
-                          cy >= 1 && cy <= g.my - 2;
-    if (interior) accumulate_window<RELAX, MATH, false>(g, p, s, me, i, lc, cy, acc);
-    else accumulate_window<RELAX, MATH, true>(g, p, s, me, i, lc, cy, acc);
+                          cy >= 1 && cy <= g.my - 2 && g.d <= 4096.0f;
+    if (interior) {
+        if (MATH == 0 && VARIANT >= 1) {
+            if (accumulate_window<RELAX, 2, false, (VARIANT == 2 ? 4 : 2)>(g, p, s, me, i, lc, cy, acc)) {
+                acc = Acc();   // a numerator outside the fast sequence's range: redo this bird with the guarded form
+                accumulate_window<RELAX, 0, false, 1>(g, p, s, me, i, lc, cy, acc);
+            }
+        } else {
+            accumulate_window<RELAX, MATH, false, 2>(g, p, s, me, i, lc, cy, acc);
+        }
+    } else {
+        accumulate_window<RELAX, MATH, true, 1>(g, p, s, me, i, lc, cy, acc);
+    }
     float xa = acc.xa, ya = acc.ya, xc = acc.xc, yc = acc.yc, xs = acc.xs, ys = acc.ys;
     const uint32_t nvec = acc.nvec;
     const int count = acc.count;
@@ -205,33 +268,27 @@ __global__ void __launch_bounds__(128) k_step(const Geom g, const Params p, cons
     out.x = toroidal_transform(__fadd_rn(me.x, dx), W);                              // :137
     out.y = toroidal_transform(__fadd_rn(me.y, dy), H);                              // :138
 
-    // Field2D::set_object_location(*self, loc) (:142-144): WRITE buffer entry i + cell counter
-    const int ncx = cell_coord(out.x, g.d, g.mx + 1);
-    const int ncy = cell_coord(out.y, g.d, g.dh);
-    const int nlc = local_col(g, ncx);
-    uint32_t key = KEY_INVALID, slot = 0;
-    if (nlc != FLK_DROP) {
-        key = (uint32_t)nlc * (uint32_t)g.dh + (uint32_t)ncy;
-        slot = atomicAdd(s.cnt + key, 1u);
-    }
-    const uint32_t w = a.out_base + i;
-    reinterpret_cast<float4 *>(s.trec)[w] = make_float4(out.x, out.y, out.ldx, out.ldy);
-    s.tid[w] = my_id;
-    s.tkey[w] = key;
-    s.tslot[w] = slot;
+    emit_successor(g, s, out, my_id, w);   // :142-144
 }
 
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st) {
     if (n_upper == 0) return;
-    const dim3 block(128), grid((n_upper + 127) / 128);
+    static const int variant = [] { const char *e = getenv("FLK_STEP_VARIANT"); return e ? atoi(e) : 1; }();
+    static const int bs = [] { const char *e = getenv("FLK_STEP_BLOCK"); return e ? atoi(e) : 128; }();
+    const dim3 block(bs), grid((n_upper + bs - 1) / bs);
+#define FLK_LAUNCH(R, M, V) k_step<R, M, V><<<grid, block, 0, st>>>(g, p, s, a)
     if (p.relax) {
-        if (a.math_mode == 0) k_step<true, 0><<<grid, block, 0, st>>>(g, p, s, a);
-        else k_step<true, 1><<<grid, block, 0, st>>>(g, p, s, a);
+        if (a.math_mode == 1) FLK_LAUNCH(true, 1, 0);
+        else if (variant == 0) FLK_LAUNCH(true, 0, 0);
+        else if (variant == 2) FLK_LAUNCH(true, 0, 2);
+        else if (variant == 3) FLK_LAUNCH(true, 0, 3);
+        else FLK_LAUNCH(true, 0, 1);
     } else {
-        if (a.math_mode == 0) k_step<false, 0><<<grid, block, 0, st>>>(g, p, s, a);
-        else k_step<false, 1><<<grid, block, 0, st>>>(g, p, s, a);
+        if (a.math_mode == 1) FLK_LAUNCH(false, 1, 0);
+        else FLK_LAUNCH(false, 0, 1);
     }
+#undef FLK_LAUNCH
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -239,13 +296,16 @@ void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ingest(const Geom g, const Store s, uint32_t n, const uint32_t *__restrict__ id,
                                                 const float2 *__restrict__ loc, const float2 *__restrict__ ld,
-                                                uint32_t base) {
+                                                uint32_t base, int owned_only) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const float2 l = loc[j], d = ld[j];
     const int cx = cell_coord(l.x, g.d, g.mx + 1);
     const int cy = cell_coord(l.y, g.d, g.dh);
-    const int lc = local_col(g, cx);
+    int lc = local_col(g, cx);
+    // strip mode: only birds this rank owns are accepted (flockers_mpi/src/model/state.rs:75-85); ghosts arrive
+    // through the halo exchange
+    if (owned_only && g.mode == 1 && (lc == 0 || lc == g.nown + 1)) lc = FLK_DROP;
     uint32_t key = KEY_INVALID, slot = 0;
     if (lc != FLK_DROP) {
         key = (uint32_t)lc * (uint32_t)g.dh + (uint32_t)cy;
@@ -258,9 +318,42 @@ __global__ void __launch_bounds__(256) k_ingest(const Geom g, const Store s, uin
 }
 
 void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id, const float2 *loc,
-                   const float2 *ld, uint32_t base, cudaStream_t st) {
+                   const float2 *ld, uint32_t base, int owned_only, cudaStream_t st) {
     if (n == 0) return;
-    k_ingest<<<(n + 255) / 256, 256, 0, st>>>(g, s, n, id, loc, ld, base);
+    k_ingest<<<(n + 255) / 256, 256, 0, st>>>(g, s, n, id, loc, ld, base, owned_only);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_unpack: birds received from the two neighbouring strips (migrants + next tick's ghosts) join the WRITE
+// buffer at [cap, cap+capx) (from the left) and [cap+capx, cap+2capx) (from the right)
+// (flockers_mpi/src/model/state.rs:128-130,167-174)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_unpack(const Geom g, const Store s) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int side = t >= s.capx;
+    const uint32_t j = side ? t - s.capx : t;
+    uint8_t *buf = side ? s.recvR : s.recvL;
+    const uint32_t n = min(reinterpret_cast<const XHdr *>(buf)->count, s.capx);
+    if (j >= n || t >= 2 * s.capx) return;
+    const float4 r = reinterpret_cast<const float4 *>(xbuf_rec(buf))[j];
+    const uint32_t id = xbuf_id(buf, s.capx)[j];
+    const int cx = cell_coord(r.x, g.d, g.mx + 1);
+    const int cy = cell_coord(r.y, g.d, g.dh);
+    const int lc = local_col(g, cx);
+    uint32_t key = KEY_INVALID, slot = 0;
+    if (lc != FLK_DROP) {
+        key = (uint32_t)lc * (uint32_t)g.dh + (uint32_t)cy;
+        slot = atomicAdd(s.cnt + key, 1u);
+    }
+    const uint32_t w = s.cap + t;
+    reinterpret_cast<float4 *>(s.trec)[w] = r;
+    s.tid[w] = id;
+    s.tkey[w] = key;
+    s.tslot[w] = slot;
+}
+
+void launch_unpack(const Geom &g, const Store &s, cudaStream_t st) {
+    k_unpack<<<(2 * s.capx + 255) / 256, 256, 0, st>>>(g, s);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -359,24 +452,46 @@ void launch_scan(const Store &s, uint32_t m, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // k_scatter / k_rank: WRITE buffer -> READ buffer in (cell, ascending id) order
 // ------------------------------------------------------------------------------------------------
+template <bool DIST>
 __global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (DIST) {
+        // valid WRITE slots: [0, n_read) stepped, [cap, cap+countL) and [cap+capx, cap+capx+countR) received
+        if (i < s.cap) {
+            if (i >= *s.n_read_dev) return;
+        } else {
+            const uint32_t t = i - s.cap;
+            if (t >= 2 * s.capx) return;
+            const uint8_t *buf = t >= s.capx ? s.recvR : s.recvL;
+            if ((t >= s.capx ? t - s.capx : t) >= min(reinterpret_cast<const XHdr *>(buf)->count, s.capx)) return;
+        }
+    } else if (i >= n) {
+        return;
+    }
     const uint32_t key = s.tkey[i];
     if (key == KEY_INVALID) return;
     const uint32_t p = s.cell_start[key] + s.tslot[i];
+    if (p >= s.cap) {
+        atomicOr(s.err_flag, ERR_CAPACITY);
+        return;
+    }
     s.sid[p] = s.tid[i];
     s.ssrc[p] = i;
     s.skey[p] = key;
 }
 
-void launch_scatter(const Store &s, uint32_t n, cudaStream_t st) {
+void launch_scatter(const Store &s, uint32_t n, int dist, cudaStream_t st) {
+    if (dist) {
+        const uint32_t tot = s.cap + 2 * s.capx;
+        k_scatter<true><<<(tot + 255) / 256, 256, 0, st>>>(s, tot);
+        return;
+    }
     if (n == 0) return;
-    k_scatter<<<(n + 255) / 256, 256, 0, st>>>(s, n);
+    k_scatter<false><<<(n + 255) / 256, 256, 0, st>>>(s, n);
 }
 
 __global__ void __launch_bounds__(256) k_rank(const Store s, uint32_t ncell, int bump_step) {
-    const uint32_t n = s.cell_start[ncell];
+    const uint32_t n = min(s.cell_start[ncell], s.cap);
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p == 0) {
         *s.n_read_dev = n;
@@ -384,7 +499,7 @@ __global__ void __launch_bounds__(256) k_rank(const Store s, uint32_t ncell, int
     }
     if (p >= n) return;
     const uint32_t key = s.skey[p];
-    const uint32_t lo = s.cell_start[key], hi = s.cell_start[key + 1];
+    const uint32_t lo = s.cell_start[key], hi = min(s.cell_start[key + 1], s.cap);
     const uint32_t my_id = s.sid[p];
     uint32_t r = 0;
     for (uint32_t q = lo; q < hi; ++q) {

@@ -23,7 +23,24 @@ struct Store {
     uint32_t *blocksum;    // scan scratch
     uint64_t *step_dev;    // tick counter used by graph replays
     uint32_t *n_read_dev;  // number of READ objects (device copy)
+    uint32_t *err_flag;    // device-side error bits (ERR_*)
+    uint32_t cap;          // READ / stepped-WRITE capacity
+    // strip decomposition only: fixed-capacity exchange buffers, XHdr | Rec[capx] | id[capx]
+    uint32_t capx;
+    uint8_t *sendL, *sendR, *recvL, *recvR;
 };
+
+constexpr uint32_t ERR_CAPACITY = 1u;   // more objects than `cap` after an exchange
+constexpr uint32_t ERR_EXCHANGE = 2u;   // more border/migrating birds than `capx`
+
+struct XHdr {
+    uint32_t count, pad0, pad1, pad2;
+};
+__host__ __device__ inline size_t xbuf_bytes(uint32_t capx) { return sizeof(XHdr) + (size_t)capx * 20; }
+__host__ __device__ inline Rec *xbuf_rec(uint8_t *b) { return reinterpret_cast<Rec *>(b + sizeof(XHdr)); }
+__host__ __device__ inline uint32_t *xbuf_id(uint8_t *b, uint32_t capx) {
+    return reinterpret_cast<uint32_t *>(b + sizeof(XHdr) + (size_t)capx * 16);
+}
 
 struct StepArgs {
     uint32_t cell_lo, cell_hi;  // step birds of cells [cell_lo, cell_hi)
@@ -34,15 +51,17 @@ struct StepArgs {
     uint32_t n_injected;        // pairs in `injected`
     uint32_t out_base;          // WRITE index of READ index 0
     int math_mode;              // 0 exact, 1 fast
+    int identity;               // 1 = re-stage every owned bird unchanged (dist commit: builds the first halo)
 };
 
 void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id, const float2 *loc,
-                   const float2 *ld, uint32_t base, cudaStream_t st);
+                   const float2 *ld, uint32_t base, int owned_only, cudaStream_t st);
+void launch_unpack(const Geom &g, const Store &s, cudaStream_t st);
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st);
 // exclusive scan of cnt -> cell_start, zeroing cnt; 3 launches
 void launch_scan(const Store &s, uint32_t ncell_plus1, cudaStream_t st);
-void launch_scatter(const Store &s, uint32_t n_write_extent, cudaStream_t st);
+void launch_scatter(const Store &s, uint32_t n_write_extent, int dist, cudaStream_t st);
 void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st);
 void launch_selftest_div2(uint64_t n, uint64_t seed, unsigned long long *mismatches, cudaStream_t st);
 void launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t st);

@@ -1,0 +1,194 @@
+"""Multi-GPU host layer: x-strip decomposition of the torus, one strip per GPU (flockers_mpi).
+
+  DistField2D   one rank per process (torchrun); NCCL send/recv inside libflk.so; torch.distributed is used
+                only to hand the NCCL unique id from rank 0 to the other ranks.
+  MgpuGroup     all strips driven by one host thread (flk_mgpu_*), peer copies instead of NCCL.
+
+Reference protocol: flockers_mpi/src/model/state.rs:51-175 and bird.rs:185-195 (owner by location, ghosts before
+the step, migration after it).  `strip_of` / `owner_of_column` restate Kdtree::get_block_by_location
+(state.rs:75, bird.rs:190) for a 1-D periodic strip partition.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .field2d import DISCRETIZATION, Field2D, _vp
+
+
+def strip_of(mx: int, world: int, rank: int) -> tuple[int, int]:
+    """global cell columns [col0, col1) owned by `rank`; the slack column mx belongs to the owner of column 0."""
+    return rank * mx // world, (rank + 1) * mx // world
+
+
+def owner_of_column(mx: int, world: int, col: int) -> int:
+    if col >= mx or col < 0:
+        return 0
+    for r in range(world):
+        c0, c1 = strip_of(mx, world, r)
+        if c0 <= col < c1:
+            return r
+    raise ValueError(col)
+
+
+def column_of(x, discretization=DISCRETIZATION) -> np.ndarray:
+    """floor(x/d) in f32, like Field2D's discretisation."""
+    q = np.floor(np.asarray(x, dtype=np.float32) / np.float32(discretization))
+    return np.nan_to_num(q, nan=0.0).astype(np.int64)
+
+
+def grid_columns(width, discretization=DISCRETIZATION) -> int:
+    return int(np.ceil(np.float32(width) / np.float32(discretization)))
+
+
+class _StripField(Field2D):
+    """shared accessors of a strip handle"""
+
+    def strip(self) -> tuple[int, int]:
+        a, b = C.c_int32(), C.c_int32()
+        check(self._L.flk_dist_strip(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def owner(self, x: float, y: float) -> int:
+        r = C.c_int32()
+        check(self._L.flk_dist_owner(self._h, x, y, C.byref(r)))
+        return r.value
+
+    def num_owned(self) -> int:
+        n = C.c_uint64()
+        check(self._L.flk_dist_num_owned(self._h, C.byref(n)))
+        return n.value
+
+    def num_objects(self) -> int:
+        # READ buffer incl. ghosts; refreshed from the device
+        ids = None
+        n = C.c_uint64()
+        check(self._L.flk_snapshot(self._h, ids, None, None, C.byref(n)))
+        return n.value
+
+    def snapshot_owned_raw(self, id_ptr, loc_ptr, ld_ptr) -> int:
+        n = C.c_uint64()
+        check(self._L.flk_dist_snapshot_owned(self._h, C.c_void_p(id_ptr), C.c_void_p(loc_ptr), C.c_void_p(ld_ptr), C.byref(n)))
+        return n.value
+
+    def snapshot_owned(self):
+        cap = self.capacity
+        ids = np.zeros(cap, dtype=np.uint32)
+        loc = np.zeros((cap, 2), dtype=np.float32)
+        ld = np.zeros((cap, 2), dtype=np.float32)
+        n = self.snapshot_owned_raw(ids.ctypes.data, loc.ctypes.data, ld.ctypes.data)
+        return ids[:n], loc[:n], ld[:n]
+
+    def binning(self):
+        ncell = (self.strip()[1] - self.strip()[0] + 3) * self.dh
+        cs = np.zeros(ncell + 1, dtype=np.uint32)
+        n = self.num_objects()
+        ids = np.zeros(max(n, 1), dtype=np.uint32)
+        check(self._L.flk_get_binning(self._h, _vp(cs), _vp(ids)))
+        return cs, ids[:n]
+
+
+class DistField2D(_StripField):
+    """One strip of the torus on this process's GPU; collective calls must be made by every rank."""
+
+    def __init__(self, width, height, discretization=DISCRETIZATION, capacity=1 << 20, device=0, rank=0, world=1):
+        import torch
+        import torch.distributed as dist
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_uint8 * 128)()
+            check(self._L.flk_dist_unique_id(buf))
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            uid = uid.cuda(device)
+        dist.broadcast(uid, src=0)
+        raw = (C.c_uint8 * 128)(*uid.cpu().tolist())
+        check(self._L.flk_dist_create(width, height, discretization, capacity, device, rank, world, raw, C.byref(self._h)))
+        self.width, self.height, self.discretization, self.toroidal = width, height, discretization, True
+        self.capacity, self.rank, self.world = capacity, rank, world
+        dw, dh, mx, my = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(self._L.flk_field_dims(self._h, C.byref(dw), C.byref(dh), C.byref(mx), C.byref(my)))
+        self.dw, self.dh, self.mx, self.my = dw.value, dh.value, mx.value, my.value
+
+    def commit(self):
+        check(self._L.flk_dist_commit(self._h))
+
+    def lazy_update(self):
+        raise _lib.FlkError(_lib.E_STATE, "a dist handle folds lazy_update into commit()/step()")
+
+    def step(self, step: int, seed: int = 0xB12D, injected: np.ndarray | None = None):
+        if injected is not None:
+            injected = np.ascontiguousarray(injected, dtype=np.float32)
+            check(self._L.flk_dist_step(self._h, step, seed, _vp(injected), injected.size // 2))
+        else:
+            check(self._L.flk_dist_step(self._h, step, seed, None, 0))
+
+
+class MgpuGroup:
+    """n strips in one process.  `devices[r]` is the CUDA ordinal of strip r (ordinals may repeat: that is how
+    the strip logic is exercised on a single GPU)."""
+
+    def __init__(self, width, height, discretization=DISCRETIZATION, capacity_per_rank=1 << 20, devices=(0, 0)):
+        self._L = _lib.load()
+        n = len(devices)
+        self.n = n
+        self._arr = (C.c_void_p * n)()
+        devs = (C.c_int * n)(*devices)
+        check(self._L.flk_mgpu_create(width, height, discretization, capacity_per_rank, n, devs, self._arr))
+        self.fields = []
+        for r in range(n):
+            f = _StripField._adopt(C.c_void_p(self._arr[r]), width, height, discretization, capacity_per_rank)
+            f.rank, f.world = r, n
+            self.fields.append(f)
+        self.mx, self.dh = self.fields[0].mx, self.fields[0].dh
+
+    def close(self):
+        for f in self.fields:
+            f.close()
+        self.fields = []
+
+    def set_params(self, **kw):
+        for f in self.fields:
+            f.set_params(**kw)
+
+    def set_math_mode(self, mode):
+        for f in self.fields:
+            f.set_math_mode(mode)
+
+    def set_objects(self, ids, loc, last_d):
+        """init scatter (flockers_mpi state.rs:51-103): every strip is offered every bird and keeps the ones it owns"""
+        for f in self.fields:
+            f.set_objects(ids, loc, last_d)
+
+    def commit(self):
+        check(self._L.flk_mgpu_commit(self._arr, self.n))
+
+    def step(self, step: int, seed: int = 0xB12D, injected: np.ndarray | None = None):
+        if injected is not None:
+            injected = np.ascontiguousarray(injected, dtype=np.float32)
+            check(self._L.flk_mgpu_step(self._arr, self.n, step, seed, _vp(injected), injected.size // 2))
+        else:
+            check(self._L.flk_mgpu_step(self._arr, self.n, step, seed, None, 0))
+
+    def run(self, first_step: int, n_steps: int, seed: int = 0xB12D):
+        check(self._L.flk_mgpu_run(self._arr, self.n, first_step, n_steps, seed))
+
+    def synchronize(self):
+        for f in self.fields:
+            f.synchronize()
+
+    def num_owned(self):
+        return [f.num_owned() for f in self.fields]
+
+    def snapshot_by_id(self):
+        parts = [f.snapshot_owned() for f in self.fields]
+        ids = np.concatenate([p[0] for p in parts])
+        loc = np.concatenate([p[1] for p in parts])
+        ld = np.concatenate([p[2] for p in parts])
+        o = np.argsort(ids, kind="stable")
+        return ids[o], loc[o], ld[o]

@@ -158,14 +158,29 @@ int flk_dist_owner(const flk_field *f, float x, float y, int32_t *rank);
 /* global cell-column range [col0,col1) owned by this rank */
 int flk_dist_strip(const flk_field *f, int32_t *col0, int32_t *col1);
 
-/* Distributed tick: before_step halo exchange + every owned Bird::step + after_step migration + update
- * (flockers_mpi/src/model/state.rs:105-175).  flk_set_objects on a dist handle accepts only birds the
- * rank owns (init scatter, state.rs:51-103, is done by the caller).  The first call performs the initial
- * halo exchange.  flk_run on a dist handle loops this. */
+/* Publish the uploaded birds and build the first halo (before_step of tick 0, state.rs:113-133).
+ * flk_set_objects on a dist handle keeps only the birds this rank owns (the init scatter, state.rs:51-103,
+ * may simply hand every rank the full list).  Collective: every rank calls it. */
+int flk_dist_commit(flk_field *f);
+
+/* Distributed tick: every owned Bird::step + ONE message per neighbour carrying the migrants (after_step,
+ * state.rs:139-175) and next tick's ghosts (before_step, state.rs:113-133) + lazy_update (state.rs:105-107).
+ * Collective.  flk_run on a dist handle loops this with Philox randomness. */
 int flk_dist_step(flk_field *f, uint64_t step, uint64_t seed, const float *injected_r, uint64_t n_injected);
 
-/* number of birds this rank owns (ghosts excluded) — synchronising */
+/* number of birds this rank owns (ghost copies excluded) — synchronising; reports capacity overflows */
 int flk_dist_num_owned(flk_field *f, uint64_t *n);
+/* flk_snapshot restricted to the birds this rank owns */
+int flk_dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n);
+
+/* ---- multi-GPU, one host thread driving n strips (single process; peer copies instead of NCCL) -------- */
+/* out[n] receives one handle per strip; devices[r] is the CUDA ordinal of strip r (ordinals may repeat). */
+int flk_mgpu_create(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
+                    const int *devices, flk_field **out);
+int flk_mgpu_commit(flk_field **handles, int n);
+int flk_mgpu_step(flk_field **handles, int n, uint64_t step, uint64_t seed, const float *injected_r,
+                  uint64_t n_injected);
+int flk_mgpu_run(flk_field **handles, int n, uint64_t first_step, uint64_t n_steps, uint64_t seed);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -1,0 +1,127 @@
+"""CPU test of the N>1 path (world_size 2 and 3 over gloo): the halo + migration protocol of flockers_mpi
+(flockers_mpi/src/model/state.rs:105-175, bird.rs:185-195), driven through the host-side partition helpers of
+examples_b200.distributed with the CPU oracle as the per-rank compute, must reproduce the single-process
+oracle bit for bit.  This is the protocol the CUDA strips implement (tests/test_gpu_strips.py checks those)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from tests.helpers import D, bits_equal, uniform_birds
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _exchange(dist, torch, O, rank, world, out_left, out_right):
+    """send one bird array to each ring neighbour, receive theirs (two messages per rank per call)"""
+    left, right = (rank - 1) % world, (rank + 1) % world
+
+    def to_t(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).copy())
+
+    res = {}
+    # sizes first, then payloads; order recvs so that world==2 pairs sendL with the peer's recvR
+    sl, sr = to_t(out_left), to_t(out_right)
+    nl, nr = torch.tensor([sl.numel()]), torch.tensor([sr.numel()])
+    rl, rr = torch.zeros(1, dtype=torch.int64), torch.zeros(1, dtype=torch.int64)
+    ops = [dist.P2POp(dist.isend, nl, left), dist.P2POp(dist.isend, nr, right),
+           dist.P2POp(dist.irecv, rr, right), dist.P2POp(dist.irecv, rl, left)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    bl, br = torch.zeros(int(rl), dtype=torch.uint8), torch.zeros(int(rr), dtype=torch.uint8)
+    ops = [dist.P2POp(dist.isend, sl, left), dist.P2POp(dist.isend, sr, right),
+           dist.P2POp(dist.irecv, br, right), dist.P2POp(dist.irecv, bl, left)]
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    res["from_left"] = bl.numpy().view(O.BIRD).copy()
+    res["from_right"] = br.numpy().view(O.BIRD).copy()
+    return res
+
+
+def _worker(rank, world, port, n, W, ticks, q):
+    import torch
+    import torch.distributed as dist
+    from examples_b200.distributed import column_of, grid_columns, owner_of_column, strip_of
+    from oracle import oracle as O
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    birds = uniform_birds(n, W, W)
+    mx = grid_columns(W, D)
+    c0, c1 = strip_of(mx, world, rank)
+    # init scatter (state.rs:51-103): every rank keeps the birds whose column it owns
+    cols = column_of(birds["x"], D)
+    mine = np.array([owner_of_column(mx, world, int(c)) == rank for c in cols])
+    sim = O.Sim(W, W)
+    sim.init(birds[mine])
+    sim.field.lazy_update()                       # Schedule::step: update(0) before tick 0
+    seed = 0xB12D
+    for t in range(ticks):
+        # before_step (state.rs:113-133): my boundary columns become the neighbours' ghosts
+        halo = _exchange(dist, torch, O, rank, world, sim.field.columns(c0, c0 + 1), sim.field.columns(c1 - 1, c1))
+        sim.field.insert_read(halo["from_left"])
+        sim.field.insert_read(halo["from_right"])
+        # every owned Bird::step; leavers reported by owner (bird.rs:190-195)
+        leavers = sim.step_strip(t, seed, None, c0, c1)
+        lcol = column_of(leavers["x"], D)
+        dest = np.array([owner_of_column(mx, world, int(c)) for c in lcol], dtype=np.int64)
+        left, right = (rank - 1) % world, (rank + 1) % world
+        to_left = leavers[dest == left] if world > 2 else leavers[(dest == left) & (lcol >= c1 if rank == 0 else lcol < c0)]
+        to_right = leavers[dest == right] if world > 2 else leavers[(dest == right) & ~((lcol >= c1) if rank == 0 else (lcol < c0))]
+        assert len(to_left) + len(to_right) == len(leavers)        # JUMP < d: leavers only reach adjacent strips
+        # after_step (state.rs:139-175): migrate
+        got = _exchange(dist, torch, O, rank, world, to_left, to_right)
+        sim.add_agents(got["from_left"])
+        sim.add_agents(got["from_right"])
+        sim.field.lazy_update()                   # update (state.rs:105-107)
+    mine_now = sim.agents()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine_now.view(np.uint8).tobytes())
+    if rank == 0:
+        allb = np.concatenate([np.frombuffer(g, dtype=O.BIRD) for g in gathered])
+        q.put(np.sort(allb, order="id").view(np.uint8).tobytes())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_and_migration_protocol_matches_single_process_oracle(world):
+    import torch.multiprocessing as mp
+    from oracle import oracle as O
+    O.build()
+    n, W, ticks = 1500, 100.0, 25
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, W, ticks, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    data = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = np.frombuffer(data, dtype=O.BIRD)
+    sim = O.Sim(W, W)
+    sim.init(uniform_birds(n, W, W))
+    for _ in range(ticks):
+        sim.step()
+    assert len(got) == n
+    assert bits_equal(got, sim.agents())
+
+
+def test_partition_helpers():
+    from examples_b200.distributed import grid_columns, owner_of_column, strip_of
+    assert grid_columns(100.0, D) == 15 and grid_columns(35840.0, D) == 5376
+    for mx, world in ((15, 2), (15, 4), (1920, 8), (5376, 8), (17, 3)):
+        edges = [strip_of(mx, world, r) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == mx
+        assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        assert all(c1 - c0 >= 2 for c0, c1 in edges)
+        for c in range(mx):
+            r = owner_of_column(mx, world, c)
+            assert edges[r][0] <= c < edges[r][1]
+        assert owner_of_column(mx, world, mx) == 0        # slack column -> owner of column 0

@@ -1,0 +1,132 @@
+"""GPU tests of the strip decomposition (flockers_mpi protocol) on ONE device: n strips driven in-process
+(flk_mgpu_*) must reproduce the single-field run bit for bit — same Philox keys (id, step) and the same
+canonical (cell, id) summation order make the result independent of which strip owns a bird."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import D, bits_equal, clustered_birds, from_arrays, to_arrays, uniform_birds
+
+pytestmark = pytest.mark.gpu
+
+
+def single(birds, W, H):
+    from examples_b200 import Field2D
+    f = Field2D(W, H, D, True, capacity=len(birds))
+    f.set_objects(*to_arrays(birds))
+    f.lazy_update()
+    return f
+
+
+def group(birds, W, H, n, cap=None):
+    from examples_b200.distributed import MgpuGroup
+    g = MgpuGroup(W, H, D, capacity_per_rank=cap or len(birds), devices=[0] * n)
+    g.set_objects(*to_arrays(birds))
+    g.commit()
+    return g
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_strips_match_single_field_shipped_config(n):
+    W = 100.0
+    birds = uniform_birds(1000, W, W)
+    f, g = single(birds, W, W), group(birds, W, W, n)
+    assert sum(g.num_owned()) == 1000
+    for t0 in range(0, 60, 10):
+        f.run(t0, 10)
+        g.run(t0, 10)
+        assert bits_equal(from_arrays(*g.snapshot_by_id()), from_arrays(*f.snapshot_by_id())), (n, t0)
+    assert sum(g.num_owned()) == 1000
+
+
+def test_strips_match_oracle_with_injected_draws():
+    W = 500.0
+    n = 20000
+    birds = uniform_birds(n, W, W)
+    g = group(birds, W, W, 4)
+    sim = O.Sim(W, W)
+    sim.init(birds)
+    rng = np.random.default_rng(9)
+    for t in range(6):
+        r = rng.random((n, 2), dtype=np.float32)
+        sim.step(injected=r)
+        g.step(t, injected=r)
+        assert bits_equal(from_arrays(*g.snapshot_by_id()), sim.agents()), t
+
+
+def test_strip_binning_is_the_global_binning_restricted_to_its_columns():
+    from examples_b200.distributed import strip_of
+    W = 300.0
+    birds = uniform_birds(6000, W, W)
+    g = group(birds, W, W, 3)
+    g.run(0, 5)
+    f = single(birds, W, W)
+    f.run(0, 5)
+    cs, ids = f.binning()
+    dh = f.dh
+    for r, sf in enumerate(g.fields):
+        c0, c1 = strip_of(f.mx, 3, r)
+        assert sf.strip() == (c0, c1)
+        lcs, lids = sf.binning()
+        # local column l (1..nown) is global column c0+l-1; ghosts: local 0 = c0-1, local nown+1 = c1 (wrapped)
+        for l in range(0, c1 - c0 + 2):
+            gc = (c0 + l - 1) % f.mx
+            want = ids[cs[gc * dh]:cs[(gc + 1) * dh]]
+            got = lids[lcs[l * dh]:lcs[(l + 1) * dh]]
+            assert np.array_equal(got, want), (r, l)
+            assert np.array_equal(np.diff(lcs[l * dh:(l + 1) * dh + 1]), np.diff(cs[gc * dh:(gc + 1) * dh + 1]))
+
+
+def test_strips_clustered_heavy_migration():
+    W = 300.0
+    birds = clustered_birds(12000, W, W, per_cluster=600, sigma=8.0)
+    f, g = single(birds, W, W), group(birds, W, W, 4)
+    for t0 in range(0, 30, 10):
+        f.run(t0, 10)
+        g.run(t0, 10)
+        assert bits_equal(from_arrays(*g.snapshot_by_id()), from_arrays(*f.snapshot_by_id())), t0
+
+
+def test_strips_slack_column_and_seam():
+    """a bird landing exactly on x == W (slack column, owned by the strip holding column 0) and birds crossing
+    the seam between the last and the first strip"""
+    W = 100.0
+    b = np.zeros(8, dtype=O.BIRD)
+    b["id"] = np.arange(8)
+    b["x"] = [0.0, 0.5, 99.5, 99.99, 1.0, 46.6, 46.7, 53.3]
+    b["y"] = [50.0, 50.5, 49.5, 50.0, 50.0, 70.0, 70.5, 70.2]
+    b["ldx"] = [-1.0, -0.5, 0.7, 0.7, 0.0, 0.7, -0.7, -0.7]
+    b["ldy"] = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.3, 0.0]
+    for kw in (dict(cohesion=0.0, avoidance=0.0, randomness=0.0, consistency=0.0, momentum=1.0, jump=1e-6), dict()):
+        f, g = single(b, W, W), group(b, W, W, 2, cap=64)
+        f.set_params(**kw)
+        g.set_params(**kw)
+        for t in range(12):
+            f.step(t)
+            f.lazy_update()
+            g.step(t)
+            assert bits_equal(from_arrays(*g.snapshot_by_id()), from_arrays(*f.snapshot_by_id())), (kw, t)
+            assert sum(g.num_owned()) == 8
+
+
+def test_capacity_overflow_after_exchange_is_reported():
+    """ghosts arriving over the halo can push a strip past its capacity: detected on the device, reported as
+    FLK_E_CAPACITY at the next synchronising call instead of corrupting memory"""
+    from examples_b200 import FlkError
+    from examples_b200.distributed import MgpuGroup, column_of, owner_of_column
+    W = 100.0
+    n = 30000
+    b = np.zeros(n, dtype=O.BIRD)
+    b["id"] = np.arange(n)
+    rng = np.random.default_rng(1)
+    b["x"] = (46.0 + rng.random(n)).astype(np.float32)       # columns 6 and 7: both sides of the 2-strip boundary
+    b["y"] = (rng.random(n) * 99).astype(np.float32)
+    g = MgpuGroup(W, W, D, capacity_per_rank=21000, devices=[0, 0])
+    own = np.array([owner_of_column(g.mx, 2, int(c)) for c in column_of(b["x"], D)])
+    for r in range(2):
+        assert (own == r).sum() <= 21000
+        g.fields[r].set_objects(*to_arrays(b[own == r]))
+    g.commit()
+    with pytest.raises(FlkError) as e:
+        g.num_owned()
+    assert e.value.code == -3
