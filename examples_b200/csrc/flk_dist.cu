@@ -137,8 +137,9 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     if (rc) { delete f; return rc; }
     f->cap = capacity;
     f->ncell = (uint32_t)g.ncols * (uint32_t)g.dh;
-    // exchange capacity: the two boundary columns hold ~2/nown of the strip; allow 8x that (clustered flocks)
-    uint64_t capx = 8 * (capacity / (uint64_t)g.nown) + 4096;
+    // exchange capacity: the two boundary columns hold ~2/nown of the strip; allow 8x that (clustered flocks).
+    // Must be identical on every rank (it fixes the message layout), hence the narrowest strip width mx/world.
+    uint64_t capx = 8 * (capacity / (uint64_t)(g.mx / world)) + 4096;
     if (capx > capacity) capx = capacity;
     f->s.capx = (uint32_t)capx;
     CUDA_TRY(cudaSetDevice(device));

@@ -1,0 +1,110 @@
+//! `GpuField2D` — a drop-in for `krabmaga::engine::fields::field_2d::Field2D<Bird>` on the Flockers hot path,
+//! plus `FlockStepper`, the single scheduled agent that replaces the per-bird `Agent::step` dispatch.
+//!
+//! Method names and argument meaning follow the reference call sites (krABMaga/examples):
+//!   new / set_object_location / lazy_update      flockers/src/model/state.rs:24,49,55
+//!   get_neighbors_within_relax_distance           flockers/src/model/bird.rs:29-31
+//!   Bird::step for every bird                     flockers/src/model/bird.rs:27-145  -> `step_all`
+//! The reference methods return no `Result`; a non-zero libflk code panics with `flk_last_error()`.
+pub mod ffi;
+
+use krabmaga::engine::agent::Agent;
+use krabmaga::engine::location::Real2D;
+use krabmaga::engine::state::State;
+use std::cell::Cell;
+use std::ffi::CStr;
+use std::ptr;
+
+/// What the field stores per object: krABMaga's `Bird { id, loc, last_d }` (bird.rs:13-18).
+pub trait FlockObject: Copy {
+    fn id(&self) -> u32;
+    fn last_d(&self) -> Real2D;
+    fn from_parts(id: u32, loc: Real2D, last_d: Real2D) -> Self;
+}
+
+fn check(rc: i32) {
+    if rc != ffi::FLK_OK {
+        let msg = unsafe { CStr::from_ptr(ffi::flk_last_error()) }.to_string_lossy().into_owned();
+        panic!("libflk error {rc}: {msg}");
+    }
+}
+
+pub struct GpuField2D<O: FlockObject> {
+    h: *mut ffi::flk_field,
+    pub width: f32,
+    pub height: f32,
+    _o: std::marker::PhantomData<O>,
+}
+
+impl<O: FlockObject> GpuField2D<O> {
+    /// `Field2D::new(w, h, discretization, toroidal)` + the capacity the device store is sized for.
+    pub fn new(width: f32, height: f32, discretization: f32, toroidal: bool, capacity: u64) -> Self {
+        let mut h = ptr::null_mut();
+        check(unsafe { ffi::flk_field_create(width, height, discretization, toroidal as i32, capacity, 0, &mut h) });
+        GpuField2D { h, width, height, _o: std::marker::PhantomData }
+    }
+    /// `&self`, like the reference (called through `downcast_ref`, bird.rs:28,142): interior mutability lives in the library.
+    pub fn set_object_location(&self, object: O, loc: Real2D) {
+        let d = object.last_d();
+        check(unsafe { ffi::flk_set_object_location(self.h, object.id(), loc.x, loc.y, d.x, d.y) });
+    }
+    pub fn get_neighbors_within_relax_distance(&self, loc: Real2D, dist: f32) -> Vec<u32> { self.query(loc, dist, true) }
+    pub fn get_neighbors_within_distance(&self, loc: Real2D, dist: f32) -> Vec<u32> { self.query(loc, dist, false) }
+    fn query(&self, loc: Real2D, dist: f32, relax: bool) -> Vec<u32> {
+        let mut ids = vec![0u32; 256];
+        loop {
+            let mut n = 0u32;
+            let rc = unsafe {
+                if relax { ffi::flk_get_neighbors_within_relax_distance(self.h, loc.x, loc.y, dist, ids.as_mut_ptr(), ids.len() as u32, &mut n) }
+                else { ffi::flk_get_neighbors_within_distance(self.h, loc.x, loc.y, dist, ids.as_mut_ptr(), ids.len() as u32, &mut n) }
+            };
+            if rc == ffi::FLK_E_CAPACITY && n as usize > ids.len() { ids.resize(n as usize, 0); continue; }
+            check(rc);
+            ids.truncate(n as usize);
+            return ids;
+        }
+    }
+    /// `Field::lazy_update` (state.rs:54-56)
+    pub fn lazy_update(&mut self) { check(unsafe { ffi::flk_lazy_update(self.h) }); }
+    /// every bird's `Bird::step` for tick `step` (bird.rs:27-145)
+    pub fn step_all(&self, step: u64, seed: u64) { check(unsafe { ffi::flk_step(self.h, step, seed, ptr::null(), 0) }); }
+    /// `Field2D::get` for every object (visualization/vis_state.rs:52)
+    pub fn get_all(&self) -> Vec<O> {
+        let mut n = 0u64;
+        check(unsafe { ffi::flk_num_objects(self.h, &mut n) });
+        let (mut id, mut loc, mut ld) = (vec![0u32; n as usize], vec![0f32; 2 * n as usize], vec![0f32; 2 * n as usize]);
+        check(unsafe { ffi::flk_snapshot(self.h, id.as_mut_ptr(), loc.as_mut_ptr(), ld.as_mut_ptr(), &mut n) });
+        (0..n as usize).map(|i| O::from_parts(id[i], Real2D { x: loc[2 * i], y: loc[2 * i + 1] }, Real2D { x: ld[2 * i], y: ld[2 * i + 1] })).collect()
+    }
+    pub fn clear(&mut self) { check(unsafe { ffi::flk_field_clear(self.h) }); }
+}
+
+impl<O: FlockObject> Drop for GpuField2D<O> {
+    fn drop(&mut self) { unsafe { ffi::flk_field_destroy(self.h) }; }
+}
+
+/// States that own a `GpuField2D` expose it (and the current tick) to the stepper.
+pub trait HasGpuField<O: FlockObject> {
+    fn gpu_field(&self) -> &GpuField2D<O>;
+    fn tick(&self) -> u64;
+}
+
+/// The one agent scheduled instead of N birds (idiom of schelling/src/model/updater.rs, forestfire/src/model/spread.rs).
+#[derive(Clone)]
+pub struct FlockStepper<S, O> {
+    pub seed: u64,
+    calls: Cell<u64>,
+    _s: std::marker::PhantomData<(S, O)>,
+}
+
+impl<S, O> FlockStepper<S, O> {
+    pub fn new(seed: u64) -> Self { FlockStepper { seed, calls: Cell::new(0), _s: std::marker::PhantomData } }
+}
+
+impl<S: State + HasGpuField<O> + 'static, O: FlockObject + 'static> Agent for FlockStepper<S, O> {
+    fn step(&mut self, state: &mut dyn State) {
+        let s = state.as_any().downcast_ref::<S>().unwrap();
+        s.gpu_field().step_all(s.tick(), self.seed);
+        self.calls.set(self.calls.get() + 1);
+    }
+}
