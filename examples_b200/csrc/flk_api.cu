@@ -41,11 +41,9 @@ int field_alloc(flk_field *f) {
     CUDA_TRY(cudaMalloc(&s.tkey, capw * 4));
     CUDA_TRY(cudaMalloc(&s.tslot, capw * 4));
     CUDA_TRY(cudaMalloc(&s.cnt, m * 4));
-    // one scratch block: (sid, ssrc, skey) during lazy_update; upload / snapshot staging otherwise
+    // one scratch block: the ranking stage (16 B/bird) during lazy_update; upload / snapshot staging otherwise
     CUDA_TRY(cudaMalloc(&f->scratch, cap * 20 + 64));
-    s.sid = reinterpret_cast<uint32_t *>(f->scratch);
-    s.ssrc = s.sid + cap;
-    s.skey = s.ssrc + cap;
+    s.stage = reinterpret_cast<uint4 *>(f->scratch);
     const uint64_t nblk = (m + 2047) / 2048 + 1;
     CUDA_TRY(cudaMalloc(&s.blocksum, nblk * 4));
     CUDA_TRY(cudaMalloc(&s.step_dev, 8));

@@ -58,34 +58,26 @@ struct Acc {
     int count = 0;       // bird.rs:50
 };
 
-// MATH: 0 = exact, guarded per pair; 1 = fast (approximate reciprocal); 2 = exact, branch-free with a sticky
-// "recompute me" flag (returned)
-template <bool RELAX, int MATH, bool SEAM, int UNROLL>
-__device__ __forceinline__ bool accumulate_window(const Geom &g, const Params &p, const Store &s, const Rec &me,
+// Generic form: any window width, wrap, seam, either query.  Used by border birds and by the exact-distance query.
+// MATH: 0 = exact (division guarded per pair, div2_rn); 1 = fast (approximate reciprocal)
+template <bool RELAX, int MATH>
+__device__ __forceinline__ void accumulate_window(const Geom &g, const Params &p, const Store &s, const Rec &me,
                                                   uint32_t i, int lc, int cy, Acc &acc) {
     const float W = g.W, H = g.H;
     const float halfW = __fdiv_rn(W, 2.0f), halfH = __fdiv_rn(H, 2.0f);
     float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
     uint32_t nvec = 0;
     int count = 0;
-    float min_num = __int_as_float(0x7f800000);
     const float4 *__restrict__ rec = reinterpret_cast<const float4 *>(s.rec);
     for_each_window_run(g, s.cell_start, lc, cy, p.k, [&](uint32_t rs, uint32_t re) {
         uint32_t j = rs;
         while (true) {
             // the caller itself is part of the query result and skipped by id (bird.rs:53): split the run at i
             const uint32_t stop = (RELAX && i >= j && i < re) ? i : re;
-#pragma unroll UNROLL
             for (; j < stop; ++j) {
                 const float4 o = __ldg(rec + j);
-                float dx, dy;
-                if (SEAM) {
-                    dx = toroidal_distance(me.x, o.x, W, halfW);   // bird.rs:54
-                    dy = toroidal_distance(me.y, o.y, H, halfH);   // bird.rs:55
-                } else {
-                    dx = __fadd_rn(me.x, -o.x);
-                    dy = __fadd_rn(me.y, -o.y);
-                }
+                const float dx = toroidal_distance(me.x, o.x, W, halfW);   // bird.rs:54
+                const float dy = toroidal_distance(me.y, o.y, H, halfH);   // bird.rs:55
                 const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));  // :59
                 if (!RELAX) {
                     // get_neighbors_within_distance keeps elem iff sqrt(dx^2+dy^2) <= dist
@@ -103,8 +95,6 @@ __device__ __forceinline__ bool accumulate_window(const Geom &g, const Params &p
                 float qa, qb;
                 if (MATH == 0) {
                     div2_rn(dx, dy, den, qa, qb);             // :60-61, two IEEE divisions
-                } else if (MATH == 2) {
-                    div2_rn_sticky(dx, dy, den, qa, qb, min_num);
                 } else {
                     float inv;
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
@@ -128,7 +118,55 @@ __device__ __forceinline__ bool accumulate_window(const Geom &g, const Params &p
     });
     acc.xa = xa; acc.ya = ya; acc.xc = xc; acc.yc = yc; acc.xs = xs; acc.ys = ys;
     acc.nvec = nvec; acc.count = count;
-    return !(min_num >= 0x1p-60f);
+}
+
+// Interior form (k == 1, no wrap, no seam): the three column runs are known without any modulo or branching, all six
+// cell_start loads are issued up front, and each run is a tight 2x-unrolled loop of 25 instructions per candidate.
+// The middle run is split at the bird's own index (bird.rs:53).  Exact arithmetic, see div2_rn_interior.
+template <int MATH>
+__device__ __forceinline__ void accumulate_run(const float4 *__restrict__ rec, uint32_t j, uint32_t e, float mx_, float my_,
+                                               float &xa, float &ya, float &xc, float &yc, float &xs, float &ys) {
+#pragma unroll 2
+    for (; j < e; ++j) {
+        const float4 o = __ldg(rec + j);
+        const float dx = __fadd_rn(mx_, -o.x);                              // bird.rs:54 (no seam in reach)
+        const float dy = __fadd_rn(my_, -o.y);                              // :55
+        const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));   // :59
+        const float den = __fadd_rn(__fmul_rn(sq, sq), 1.0f);
+        float qa, qb;
+        if (MATH == 1) {
+            float inv;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+            qa = __fmul_rn(dx, inv);
+            qb = __fmul_rn(dy, inv);
+        } else {
+            div2_rn_interior(dx, dy, den, qa, qb);                          // :60-61
+        }
+        xa = __fadd_rn(xa, qa);
+        ya = __fadd_rn(ya, qb);
+        xc = __fadd_rn(xc, dx);      // :64
+        yc = __fadd_rn(yc, dy);      // :65
+        xs = __fadd_rn(xs, o.z);     // :68
+        ys = __fadd_rn(ys, o.w);     // :69
+    }
+}
+
+template <int MATH>
+__device__ __forceinline__ void accumulate_interior(const Geom &g, const Store &s, const Rec &me, uint32_t i, int lc,
+                                                    int cy, Acc &acc) {
+    const float4 *__restrict__ rec = reinterpret_cast<const float4 *>(s.rec);
+    const uint32_t *__restrict__ cs = s.cell_start + (uint32_t)(lc - 1) * (uint32_t)g.dh + (uint32_t)(cy - 1);
+    const uint32_t a0 = __ldg(cs), b0 = __ldg(cs + 3);
+    const uint32_t a1 = __ldg(cs + g.dh), b1 = __ldg(cs + g.dh + 3);
+    const uint32_t a2 = __ldg(cs + 2 * g.dh), b2 = __ldg(cs + 2 * g.dh + 3);
+    float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
+    accumulate_run<MATH>(rec, a0, b0, me.x, me.y, xa, ya, xc, yc, xs, ys);
+    accumulate_run<MATH>(rec, a1, i, me.x, me.y, xa, ya, xc, yc, xs, ys);       // own cell is in the middle run
+    accumulate_run<MATH>(rec, i + 1, b1, me.x, me.y, xa, ya, xc, yc, xs, ys);
+    accumulate_run<MATH>(rec, a2, b2, me.x, me.y, xa, ya, xc, yc, xs, ys);
+    acc.xa = xa; acc.ya = ya; acc.xc = xc; acc.yc = yc; acc.xs = xs; acc.ys = ys;
+    acc.nvec = (b0 - a0) + (b1 - a1) + (b2 - a2);
+    acc.count = (int)acc.nvec - 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -147,9 +185,10 @@ __device__ __forceinline__ void xbuf_append(const Store &s, uint8_t *buf, const 
     }
 }
 
-__device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, const Rec &out, uint32_t id, uint32_t w) {
-    const int ncx = cell_coord(out.x, g.d, g.mx + 1);
-    const int ncy = cell_coord(out.y, g.d, g.dh);
+__device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, const Rec &out, uint32_t id, uint32_t w,
+                                               bool d_ok, const Recip &Rd) {
+    const int ncx = d_ok ? cell_coord_fast(out.x, Rd, g.mx + 1) : cell_coord(out.x, g.d, g.mx + 1);
+    const int ncy = d_ok ? cell_coord_fast(out.y, Rd, g.dh) : cell_coord(out.y, g.d, g.dh);
     const int nlc = local_col(g, ncx);
     uint32_t key = KEY_INVALID, slot = 0;
     if (nlc != FLK_DROP) {
@@ -169,8 +208,8 @@ __device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, co
 // ------------------------------------------------------------------------------------------------
 // k_step
 // ------------------------------------------------------------------------------------------------
-template <bool RELAX, int MATH, int VARIANT>
-__global__ void __launch_bounds__(256, (VARIANT == 3 ? 5 : 4)) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
+template <bool RELAX, int MATH>
+__global__ void __launch_bounds__(256, 6) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
     const uint32_t lo = __ldg(s.cell_start + a.cell_lo);
     const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
     const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,8 +220,10 @@ __global__ void __launch_bounds__(256, (VARIANT == 3 ? 5 : 4)) k_step(const Geom
     const float W = g.W, H = g.H;
 
     // cell of this bird (same arithmetic as the binning that placed it)
-    const int gcx = cell_coord(me.x, g.d, g.mx + 1);
-    const int cy = cell_coord(me.y, g.d, g.dh);
+    const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
+    const Recip Rd = make_recip(g.d);
+    const int gcx = d_ok ? cell_coord_fast(me.x, Rd, g.mx + 1) : cell_coord(me.x, g.d, g.mx + 1);
+    const int cy = d_ok ? cell_coord_fast(me.y, Rd, g.dh) : cell_coord(me.y, g.d, g.dh);
     const int lc = local_col(g, gcx);
     const uint32_t w = a.out_base + i;
     if (g.mode == 1 && (lc == 0 || lc == g.nown + 1)) {
@@ -191,7 +232,7 @@ __global__ void __launch_bounds__(256, (VARIANT == 3 ? 5 : 4)) k_step(const Geom
         return;
     }
     if (a.identity) {
-        emit_successor(g, s, me, my_id, w);
+        emit_successor(g, s, me, my_id, w, d_ok, Rd);
         return;
     }
 
@@ -199,19 +240,9 @@ __global__ void __launch_bounds__(256, (VARIANT == 3 ? 5 : 4)) k_step(const Geom
     // Birds whose 3x3 window cannot touch the seam never take the |a-b| > dim/2 branch of toroidal_distance:
     // cells are < 2d apart and dim >= 6d, so the plain difference is the toroidal one (exactly).
     const bool interior = g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && gcx >= 1 && gcx <= g.mx - 2 &&
-                          cy >= 1 && cy <= g.my - 2 && g.d <= 4096.0f;
-    if (interior) {
-        if (MATH == 0 && VARIANT >= 1) {
-            if (accumulate_window<RELAX, 2, false, (VARIANT == 2 ? 4 : 2)>(g, p, s, me, i, lc, cy, acc)) {
-                acc = Acc();   // a numerator outside the fast sequence's range: redo this bird with the guarded form
-                accumulate_window<RELAX, 0, false, 1>(g, p, s, me, i, lc, cy, acc);
-            }
-        } else {
-            accumulate_window<RELAX, MATH, false, 2>(g, p, s, me, i, lc, cy, acc);
-        }
-    } else {
-        accumulate_window<RELAX, MATH, true, 1>(g, p, s, me, i, lc, cy, acc);
-    }
+                          cy >= 1 && cy <= g.my - 2 && d_ok;
+    if (interior && RELAX) accumulate_interior<MATH>(g, s, me, i, lc, cy, acc);
+    else accumulate_window<RELAX, MATH>(g, p, s, me, i, lc, cy, acc);
     float xa = acc.xa, ya = acc.ya, xc = acc.xc, yc = acc.yc, xs = acc.xs, ys = acc.ys;
     const uint32_t nvec = acc.nvec;
     const int count = acc.count;
@@ -221,15 +252,26 @@ __global__ void __launch_bounds__(256, (VARIANT == 3 ? 5 : 4)) k_step(const Geom
     if (nvec != 0) {                                                  // :42
         if (count > 0) {                                              // :73
             const float c = (float)count;
-            xa = __fdiv_rn(xa, c); ya = __fdiv_rn(ya, c);             // :74-75
-            xc = __fdiv_rn(xc, c); yc = __fdiv_rn(yc, c);             // :76-77
-            xs = __fdiv_rn(xs, c); ys = __fdiv_rn(ys, c);             // :78-79
-            con_x = __fdiv_rn(xs, c); con_y = __fdiv_rn(ys, c);       // :81-84 (second division, kept)
+            // eight divisions by `count` (:74-84): one shared reciprocal when all six sums are in the safe range
+            const float lo = fminf(fminf(fminf(fabsf(xa), fabsf(ya)), fminf(fabsf(xc), fabsf(yc))), fminf(fabsf(xs), fabsf(ys)));
+            const float hi = fmaxf(fmaxf(fmaxf(fabsf(xa), fabsf(ya)), fmaxf(fabsf(xc), fabsf(yc))), fmaxf(fabsf(xs), fabsf(ys)));
+            if (lo >= 0x1p-60f && hi <= 0x1p60f) {
+                const Recip R = make_recip(c);                        // c in [1, 2^24]
+                xa = div_rn_fast(xa, R); ya = div_rn_fast(ya, R);     // :74-75
+                xc = div_rn_fast(xc, R); yc = div_rn_fast(yc, R);     // :76-77
+                xs = div_rn_fast(xs, R); ys = div_rn_fast(ys, R);     // :78-79
+                con_x = div_rn_fast(xs, R); con_y = div_rn_fast(ys, R);   // :81-84 (second division, kept)
+            } else {
+                xa = __fdiv_rn(xa, c); ya = __fdiv_rn(ya, c);
+                xc = __fdiv_rn(xc, c); yc = __fdiv_rn(yc, c);
+                xs = __fdiv_rn(xs, c); ys = __fdiv_rn(ys, c);
+                con_x = __fdiv_rn(xs, c); con_y = __fdiv_rn(ys, c);
+            }
         } else {
             con_x = xs; con_y = ys;                                   // :85-90
         }
         avo_x = __fmul_rn(400.0f, xa); avo_y = __fmul_rn(400.0f, ya); // :92-95
-        coh_x = __fdiv_rn(-xc, 10.0f); coh_y = __fdiv_rn(-yc, 10.0f); // :97-100
+        div2_rn_checked(-xc, -yc, 10.0f, coh_x, coh_y);               // :97-100
         float r1, r2;                                                 // :103-107
         if (a.injected != nullptr && my_id < a.n_injected) {
             const float2 r = __ldg(a.injected + my_id);
@@ -244,8 +286,7 @@ __global__ void __launch_bounds__(256, (VARIANT == 3 ? 5 : 4)) k_step(const Geom
         const float xr = __fadd_rn(__fmul_rn(r1, 2.0f), -1.0f);
         const float yr = __fadd_rn(__fmul_rn(r2, 2.0f), -1.0f);
         const float sq = __fsqrt_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(yr, yr)));   // :109
-        rnd_x = __fdiv_rn(__fmul_rn(0.05f, xr), sq);                  // :110-113
-        rnd_y = __fdiv_rn(__fmul_rn(0.05f, yr), sq);
+        div2_rn_checked(__fmul_rn(0.05f, xr), __fmul_rn(0.05f, yr), sq, rnd_x, rnd_y);  // :110-113
     }
     // :116-127, summed left to right
     float dx = __fmul_rn(p.cohesion, coh_x);
@@ -260,33 +301,31 @@ __global__ void __launch_bounds__(256, (VARIANT == 3 ? 5 : 4)) k_step(const Geom
     dy = __fadd_rn(dy, __fmul_rn(p.momentum, me.ldy));
     const float dis = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));   // :129
     if (dis > 0.0f) {                                                                // :130
-        dx = __fmul_rn(__fdiv_rn(dx, dis), p.jump);                                  // :131
-        dy = __fmul_rn(__fdiv_rn(dy, dis), p.jump);                                  // :132
+        float ux, uy;
+        div2_rn_checked(dx, dy, dis, ux, uy);
+        dx = __fmul_rn(ux, p.jump);                                                  // :131
+        dy = __fmul_rn(uy, p.jump);                                                  // :132
     }
     Rec out;
     out.ldx = dx; out.ldy = dy;                                                      // :135
     out.x = toroidal_transform(__fadd_rn(me.x, dx), W);                              // :137
     out.y = toroidal_transform(__fadd_rn(me.y, dy), H);                              // :138
 
-    emit_successor(g, s, out, my_id, w);   // :142-144
+    emit_successor(g, s, out, my_id, w, d_ok, Rd);   // :142-144
 }
 
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st) {
     if (n_upper == 0) return;
-    static const int variant = [] { const char *e = getenv("FLK_STEP_VARIANT"); return e ? atoi(e) : 1; }();
     static const int bs = [] { const char *e = getenv("FLK_STEP_BLOCK"); return e ? atoi(e) : 128; }();
     const dim3 block(bs), grid((n_upper + bs - 1) / bs);
-#define FLK_LAUNCH(R, M, V) k_step<R, M, V><<<grid, block, 0, st>>>(g, p, s, a)
+#define FLK_LAUNCH(R, M) k_step<R, M><<<grid, block, 0, st>>>(g, p, s, a)
     if (p.relax) {
-        if (a.math_mode == 1) FLK_LAUNCH(true, 1, 0);
-        else if (variant == 0) FLK_LAUNCH(true, 0, 0);
-        else if (variant == 2) FLK_LAUNCH(true, 0, 2);
-        else if (variant == 3) FLK_LAUNCH(true, 0, 3);
-        else FLK_LAUNCH(true, 0, 1);
+        if (a.math_mode == 1) FLK_LAUNCH(true, 1);
+        else FLK_LAUNCH(true, 0);
     } else {
-        if (a.math_mode == 1) FLK_LAUNCH(false, 1, 0);
-        else FLK_LAUNCH(false, 0, 1);
+        if (a.math_mode == 1) FLK_LAUNCH(false, 1);
+        else FLK_LAUNCH(false, 0);
     }
 #undef FLK_LAUNCH
 }
@@ -475,9 +514,7 @@ __global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n) {
         atomicOr(s.err_flag, ERR_CAPACITY);
         return;
     }
-    s.sid[p] = s.tid[i];
-    s.ssrc[p] = i;
-    s.skey[p] = key;
+    s.stage[p] = make_uint4(s.tid[i], i, key, 0u);   // one 16-byte store instead of three scattered 4-byte ones
 }
 
 void launch_scatter(const Store &s, uint32_t n, int dist, cudaStream_t st) {
@@ -498,16 +535,17 @@ __global__ void __launch_bounds__(256) k_rank(const Store s, uint32_t ncell, int
         if (bump_step) *s.step_dev += 1;
     }
     if (p >= n) return;
-    const uint32_t key = s.skey[p];
+    const uint4 mine = s.stage[p];
+    const uint32_t key = mine.z;
     const uint32_t lo = s.cell_start[key], hi = min(s.cell_start[key + 1], s.cap);
-    const uint32_t my_id = s.sid[p];
+    const uint32_t my_id = mine.x;
     uint32_t r = 0;
     for (uint32_t q = lo; q < hi; ++q) {
-        const uint32_t other = s.sid[q];
+        const uint32_t other = s.stage[q].x;
         r += (other < my_id) || (other == my_id && q < p);
     }
     const uint32_t dst = lo + r;
-    reinterpret_cast<float4 *>(s.rec)[dst] = reinterpret_cast<const float4 *>(s.trec)[s.ssrc[p]];
+    reinterpret_cast<float4 *>(s.rec)[dst] = reinterpret_cast<const float4 *>(s.trec)[mine.y];
     s.ids[dst] = my_id;
 }
 

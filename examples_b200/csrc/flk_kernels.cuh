@@ -17,9 +17,7 @@ struct Store {
     uint32_t *tkey;        // WRITE local cell key (KEY_INVALID = not kept on this GPU)
     uint32_t *tslot;       // WRITE arrival slot inside its cell
     uint32_t *cnt;         // WRITE per-cell counters (ncell+1)
-    uint32_t *sid;         // staging for the (cell,id) ranking
-    uint32_t *ssrc;
-    uint32_t *skey;
+    uint4 *stage;          // staging for the (cell,id) ranking: {id, WRITE index, cell key, -} in cell order
     uint32_t *blocksum;    // scan scratch
     uint64_t *step_dev;    // tick counter used by graph replays
     uint32_t *n_read_dev;  // number of READ objects (device copy)
