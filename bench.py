@@ -239,6 +239,10 @@ def run_ours(args, world: int, rank: int, local_rank: int):
         x0 = float(np.float32(c0) * np.float32(D))
         x1 = float(np.float32(c1) * np.float32(D)) if c1 < gx else W
         loc = make_birds(n_local, W, H, clustered, x0, x1, seed=INIT_SEED + rank)
+        # f32 rounding at the strip edges: keep every generated bird inside the columns this rank owns
+        col = fdist.column_of(loc[:, 0], D)
+        off = (col < c0) | (col >= c1)
+        loc[off, 0] = np.float32(0.5 * (x0 + x1))
         id_base = rank * n_local
     # pinned host buffers: the host-side copy of the agents (what krABMaga's Schedule holds)
     h_id = torch.arange(id_base, id_base + n_local, dtype=torch.int64).to(torch.uint32).pin_memory() \
@@ -251,6 +255,7 @@ def run_ours(args, world: int, rank: int, local_rank: int):
     f.set_math_mode(args.math)
     f.commit()  # lazy_update (+ first halo exchange on >1 GPU)
     f.synchronize()
+    assert f.num_owned() == n_local, (f.num_owned(), n_local)
 
     # ---- warm-up ----
     f.run(0, args.warmup, STEP_SEED)

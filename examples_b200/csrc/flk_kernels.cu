@@ -208,45 +208,37 @@ __device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, co
 // ------------------------------------------------------------------------------------------------
 // k_step
 // ------------------------------------------------------------------------------------------------
-template <bool RELAX, int MATH>
-__global__ void __launch_bounds__(256, 6) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
-    const uint32_t lo = __ldg(s.cell_start + a.cell_lo);
-    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
-    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= hi) return;
+// ---- TMA staging helpers (1-D bulk copies global -> shared, completion on an mbarrier) -------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
-    const Rec me = s.rec[i];
-    const uint32_t my_id = s.ids[i];
+constexpr int TILE_CAP = 256;   // records staged per window column (4 KB); 3 columns = 12 KB per CTA
+
+// everything of Bird::step after the neighbour loop (bird.rs:73-145) + set_object_location
+template <int MATH>
+__device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, const Store &s, const StepArgs &a, const Rec &me,
+                                            uint32_t my_id, uint32_t w, const Acc &acc, bool d_ok, const Recip &Rd) {
     const float W = g.W, H = g.H;
-
-    // cell of this bird (same arithmetic as the binning that placed it)
-    const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
-    const Recip Rd = make_recip(g.d);
-    const int gcx = d_ok ? cell_coord_fast(me.x, Rd, g.mx + 1) : cell_coord(me.x, g.d, g.mx + 1);
-    const int cy = d_ok ? cell_coord_fast(me.y, Rd, g.dh) : cell_coord(me.y, g.d, g.dh);
-    const int lc = local_col(g, gcx);
-    const uint32_t w = a.out_base + i;
-    if (g.mode == 1 && (lc == 0 || lc == g.nown + 1)) {
-        // ghost copy (flockers_mpi: received_neighbors): stepped by its owner, dropped here
-        s.tkey[w] = KEY_INVALID;
-        return;
-    }
-    if (a.identity) {
-        emit_successor(g, s, me, my_id, w, d_ok, Rd);
-        return;
-    }
-
-    Acc acc;
-    // Birds whose 3x3 window cannot touch the seam never take the |a-b| > dim/2 branch of toroidal_distance:
-    // cells are < 2d apart and dim >= 6d, so the plain difference is the toroidal one (exactly).
-    const bool interior = g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && gcx >= 1 && gcx <= g.mx - 2 &&
-                          cy >= 1 && cy <= g.my - 2 && d_ok;
-    if (interior && RELAX) accumulate_interior<MATH>(g, s, me, i, lc, cy, acc);
-    else accumulate_window<RELAX, MATH>(g, p, s, me, i, lc, cy, acc);
     float xa = acc.xa, ya = acc.ya, xc = acc.xc, yc = acc.yc, xs = acc.xs, ys = acc.ys;
     const uint32_t nvec = acc.nvec;
     const int count = acc.count;
-
     float avo_x = 0.0f, avo_y = 0.0f, coh_x = 0.0f, coh_y = 0.0f;   // bird.rs:36-40
     float rnd_x = 0.0f, rnd_y = 0.0f, con_x = 0.0f, con_y = 0.0f;
     if (nvec != 0) {                                                  // :42
@@ -314,18 +306,150 @@ __global__ void __launch_bounds__(256, 6) k_step(const Geom g, const Params p, c
     emit_successor(g, s, out, my_id, w, d_ok, Rd);   // :142-144
 }
 
+// interior accumulation out of the CTA's shared-memory tile (same order, same arithmetic as accumulate_interior)
+template <int MATH>
+__device__ __forceinline__ void accumulate_run_smem(const float4 *tile, uint32_t j, uint32_t e, float mx_, float my_,
+                                                    float &xa, float &ya, float &xc, float &yc, float &xs, float &ys) {
+#pragma unroll 2
+    for (; j < e; ++j) {
+        const float4 o = tile[j];
+        const float dx = __fadd_rn(mx_, -o.x);                              // bird.rs:54 (no seam in reach)
+        const float dy = __fadd_rn(my_, -o.y);                              // :55
+        const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));   // :59
+        const float den = __fadd_rn(__fmul_rn(sq, sq), 1.0f);
+        float qa, qb;
+        if (MATH == 1) {
+            float inv;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+            qa = __fmul_rn(dx, inv);
+            qb = __fmul_rn(dy, inv);
+        } else {
+            div2_rn_interior(dx, dy, den, qa, qb);                          // :60-61
+        }
+        xa = __fadd_rn(xa, qa);
+        ya = __fadd_rn(ya, qb);
+        xc = __fadd_rn(xc, dx);      // :64
+        yc = __fadd_rn(yc, dy);      // :65
+        xs = __fadd_rn(xs, o.z);     // :68
+        ys = __fadd_rn(ys, o.w);     // :69
+    }
+}
+
+// k_step: one thread per READ bird.  TILE = stage the CTA's three window-column runs in shared memory with TMA bulk
+// copies when the CTA's birds sit in one interior column (the common case); other CTAs read through L1.
+template <bool RELAX, int MATH, bool TILE>
+__global__ void __launch_bounds__(128, 12) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
+    __shared__ __align__(128) float4 tile[TILE ? 3 : 1][TILE ? TILE_CAP : 1];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int shc[5];
+
+    const uint32_t lo = __ldg(s.cell_start + a.cell_lo);
+    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
+    const uint32_t first = lo + blockIdx.x * blockDim.x;
+    if (first >= hi) return;                       // whole CTA out of range
+    const uint32_t i = first + threadIdx.x;
+    const bool valid = i < hi;
+
+    Rec me = Rec{0.f, 0.f, 0.f, 0.f};
+    uint32_t my_id = 0;
+    // cell of this bird (same arithmetic as the binning that placed it)
+    const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
+    const Recip Rd = make_recip(g.d);
+    int gcx = 0, cy = 0, lc = 0;
+    if (valid) {
+        me = s.rec[i];
+        my_id = s.ids[i];
+        gcx = d_ok ? cell_coord_fast(me.x, Rd, g.mx + 1) : cell_coord(me.x, g.d, g.mx + 1);
+        cy = d_ok ? cell_coord_fast(me.y, Rd, g.dh) : cell_coord(me.y, g.d, g.dh);
+        lc = local_col(g, gcx);
+    }
+
+    bool use_tile = false;
+    uint32_t sA0 = 0, sA1 = 0, sA2 = 0;
+    if (TILE) {
+        const uint32_t last = min(first + blockDim.x, hi) - 1;
+        if (threadIdx.x == 0) {
+            shc[0] = lc; shc[1] = cy; shc[4] = gcx;
+            mbar_init(&bar, 1);
+        }
+        if (i == last) { shc[2] = lc; shc[3] = cy; }
+        __syncthreads();
+        const int lcA = shc[0], cyA = shc[1], lcB = shc[2], cyB = shc[3], gcxA = shc[4];
+        bool eligible = RELAX && !a.identity && g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && d_ok &&
+                        lcA == lcB && gcxA >= 1 && gcxA <= g.mx - 2 && cyA >= 1 && cyB <= g.my - 2 && cyA <= cyB &&
+                        (g.mode == 0 || (lcA >= 1 && lcA <= g.nown));
+        uint32_t len0 = 0, len1 = 0, len2 = 0;
+        if (eligible) {
+            const uint32_t *cs = s.cell_start + (uint32_t)(lcA - 1) * (uint32_t)g.dh;
+            sA0 = __ldg(cs + cyA - 1);            len0 = __ldg(cs + cyB + 2) - sA0;
+            sA1 = __ldg(cs + g.dh + cyA - 1);     len1 = __ldg(cs + g.dh + cyB + 2) - sA1;
+            sA2 = __ldg(cs + 2 * g.dh + cyA - 1); len2 = __ldg(cs + 2 * g.dh + cyB + 2) - sA2;
+            eligible = len0 <= TILE_CAP && len1 <= TILE_CAP && len2 <= TILE_CAP;
+        }
+        if (eligible) {   // CTA-uniform
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar, (len0 + len1 + len2) * 16u);
+                const float4 *rec = reinterpret_cast<const float4 *>(s.rec);
+                if (len0) tma_load_1d(&tile[0][0], rec + sA0, len0 * 16u, &bar);
+                if (len1) tma_load_1d(&tile[1][0], rec + sA1, len1 * 16u, &bar);
+                if (len2) tma_load_1d(&tile[2][0], rec + sA2, len2 * 16u, &bar);
+            }
+            mbar_wait(&bar, 0);
+            use_tile = true;
+        }
+    }
+    if (!valid) return;
+
+    const uint32_t w = a.out_base + i;
+    if (g.mode == 1 && (lc == 0 || lc == g.nown + 1)) {
+        // ghost copy (flockers_mpi: received_neighbors): stepped by its owner, dropped here
+        s.tkey[w] = KEY_INVALID;
+        return;
+    }
+    if (a.identity) {
+        emit_successor(g, s, me, my_id, w, d_ok, Rd);
+        return;
+    }
+
+    Acc acc;
+    if (TILE && use_tile) {
+        // this bird's three runs, as offsets into the staged column runs
+        const uint32_t *cs = s.cell_start + (uint32_t)(lc - 1) * (uint32_t)g.dh + (uint32_t)(cy - 1);
+        const uint32_t a0 = __ldg(cs), b0 = __ldg(cs + 3);
+        const uint32_t a1 = __ldg(cs + g.dh), b1 = __ldg(cs + g.dh + 3);
+        const uint32_t a2 = __ldg(cs + 2 * g.dh), b2 = __ldg(cs + 2 * g.dh + 3);
+        float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
+        accumulate_run_smem<MATH>(tile[0], a0 - sA0, b0 - sA0, me.x, me.y, xa, ya, xc, yc, xs, ys);
+        accumulate_run_smem<MATH>(tile[1], a1 - sA1, i - sA1, me.x, me.y, xa, ya, xc, yc, xs, ys);   // split at self
+        accumulate_run_smem<MATH>(tile[1], i + 1 - sA1, b1 - sA1, me.x, me.y, xa, ya, xc, yc, xs, ys);
+        accumulate_run_smem<MATH>(tile[2], a2 - sA2, b2 - sA2, me.x, me.y, xa, ya, xc, yc, xs, ys);
+        acc.xa = xa; acc.ya = ya; acc.xc = xc; acc.yc = yc; acc.xs = xs; acc.ys = ys;
+        acc.nvec = (b0 - a0) + (b1 - a1) + (b2 - a2);
+        acc.count = (int)acc.nvec - 1;
+    } else {
+        // Birds whose 3x3 window cannot touch the seam never take the |a-b| > dim/2 branch of toroidal_distance:
+        // cells are < 2d apart and dim >= 6d, so the plain difference is the toroidal one (exactly).
+        const bool interior = g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && gcx >= 1 && gcx <= g.mx - 2 &&
+                              cy >= 1 && cy <= g.my - 2 && d_ok;
+        if (interior && RELAX) accumulate_interior<MATH>(g, s, me, i, lc, cy, acc);
+        else accumulate_window<RELAX, MATH>(g, p, s, me, i, lc, cy, acc);
+    }
+    finish_bird<MATH>(g, p, s, a, me, my_id, w, acc, d_ok, Rd);
+}
+
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st) {
     if (n_upper == 0) return;
-    static const int bs = [] { const char *e = getenv("FLK_STEP_BLOCK"); return e ? atoi(e) : 128; }();
+    static const int tile = [] { const char *e = getenv("FLK_STEP_TILE"); return e ? atoi(e) : 1; }();
+    const int bs = 128;
     const dim3 block(bs), grid((n_upper + bs - 1) / bs);
-#define FLK_LAUNCH(R, M) k_step<R, M><<<grid, block, 0, st>>>(g, p, s, a)
+#define FLK_LAUNCH(R, M, T) k_step<R, M, T><<<grid, block, 0, st>>>(g, p, s, a)
     if (p.relax) {
-        if (a.math_mode == 1) FLK_LAUNCH(true, 1);
-        else FLK_LAUNCH(true, 0);
+        if (a.math_mode == 1) { if (tile) FLK_LAUNCH(true, 1, true); else FLK_LAUNCH(true, 1, false); }
+        else { if (tile) FLK_LAUNCH(true, 0, true); else FLK_LAUNCH(true, 0, false); }
     } else {
-        if (a.math_mode == 1) FLK_LAUNCH(false, 1);
-        else FLK_LAUNCH(false, 0);
+        if (a.math_mode == 1) FLK_LAUNCH(false, 1, false);
+        else FLK_LAUNCH(false, 0, false);
     }
 #undef FLK_LAUNCH
 }

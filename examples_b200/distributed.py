@@ -165,6 +165,20 @@ class MgpuGroup:
         for f in self.fields:
             f.set_objects(ids, loc, last_d)
 
+    def scatter_objects(self, ids, loc, last_d):
+        """init scatter done on the host like flockers_mpi's rank 0 (state.rs:65-92): every bird goes to the strip
+        that owns its cell column (needs only capacity_per_rank >= the strip's own population)"""
+        ids = np.asarray(ids)
+        loc = np.asarray(loc, dtype=np.float32).reshape(-1, 2)
+        last_d = np.asarray(last_d, dtype=np.float32).reshape(-1, 2)
+        col = column_of(loc[:, 0], self.fields[0].discretization)
+        for r, f in enumerate(self.fields):
+            c0, c1 = strip_of(self.mx, self.n, r)
+            m = (col >= c0) & (col < c1)
+            if r == 0:
+                m |= col >= self.mx
+            f.set_objects(ids[m], loc[m], last_d[m])
+
     def commit(self):
         check(self._L.flk_mgpu_commit(self._arr, self.n))
 
