@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libflk.so")
+LIB_PATH = os.environ.get("FLK_LIB") or os.path.join(HERE, "libflk.so")   # FLK_LIB: tuning builds only
 
 OK, E_INVALID, E_CUDA, E_CAPACITY, E_UNSUPPORTED, E_NCCL, E_STATE = 0, -1, -2, -3, -4, -5, -6
 

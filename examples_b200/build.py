@@ -43,7 +43,9 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = os.environ.get("FLK_NVCC_EXTRA", "").split()   # tuning experiments only, e.g. -DFLK_SMEM_UNROLL=4
+    out = os.environ.get("FLK_LIB_OUT", LIB)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     env = dict(os.environ)
     # the image exports CC=/opt/gcc/bin/gcc (no libgomp spec); nvcc's host compiler must be the system one
     res = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else cmd,

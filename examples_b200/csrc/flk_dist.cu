@@ -16,6 +16,7 @@
 //          buffers, ordered with events.  Also how the strip logic is tested on a single GPU.
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/flk.h"
@@ -82,9 +83,10 @@ struct flk_dist_state {
     int left = 0, right = 0;
     uint8_t *xbuf = nullptr;           // sendL | sendR | recvL | recvR
     flk_field **group = nullptr;       // LOCAL: all handles of the group (owned by rank 0's state)
-    cudaEvent_t ev_sent = nullptr;     // my send buffers are complete
-    cudaEvent_t ev_copied = nullptr;   // I have copied my neighbours' send buffers
-    bool copied_valid = false;
+    cudaStream_t comm_stream = nullptr;   // high-priority stream the exchange runs on, beside the interior step
+    cudaEvent_t ev_sent = nullptr;     // my send buffers are complete (border columns stepped)
+    cudaEvent_t ev_copied = nullptr;   // the exchange is complete: neighbours' messages are in my recv buffers
+    bool overlap = true;               // FLK_DIST_OVERLAP=0 steps all columns before the exchange (A/B measurements)
     bool committed = false;
 };
 
@@ -95,6 +97,7 @@ void dist_free(flk_field *f) {
     if (!d) return;
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     if (d->xbuf) cudaFree(d->xbuf);
+    if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
     if (d->ev_sent) cudaEventDestroy(d->ev_sent);
     if (d->ev_copied) cudaEventDestroy(d->ev_copied);
     if (d->rank == 0 && d->group) delete[] d->group;
@@ -151,11 +154,17 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     flk_dist_state *d = new flk_dist_state();
     f->dist = d;
     d->rank = rank; d->world = world; d->transport = transport;
+    if (const char *e = getenv("FLK_DIST_OVERLAP")) d->overlap = atoi(e) != 0;
     d->left = (rank + world - 1) % world;
     d->right = (rank + 1) % world;
     const size_t xb = (xbuf_bytes(f->s.capx) + 255) & ~(size_t)255;
     cudaError_t e = cudaMalloc(&d->xbuf, 4 * xb);
     if (e == cudaSuccess) e = cudaMemsetAsync(d->xbuf, 0, 4 * xb, f->stream);
+    if (e == cudaSuccess) {
+        int lo_p = 0, hi_p = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+        e = cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, hi_p);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_sent, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -168,19 +177,16 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     return FLK_OK;
 }
 
-// phase 1 of a tick on one strip: clear the outgoing messages, step (or re-stage) every owned bird
+// phase 1 of a tick on one strip: clear the outgoing messages, step (or re-stage) every owned bird.
+// Successors that go into a message can only come from the two owned columns next to each boundary (a bird moves
+// less than one column per tick) and from the slack column, so those columns are stepped FIRST; the exchange then
+// runs on the comm stream while the interior columns are stepped (north star: halo exchange overlapped with
+// interior-cell compute on separate streams).
 static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const float2 *d_inj, uint32_t n_inj, int identity) {
     flk_dist_state *d = f->dist;
-    if (d->transport == 1 && d->copied_valid) {
-        // my neighbours read my send buffers last tick: wait until their copies are done
-        flk_field **grp = d->group;
-        CUDA_TRY(cudaStreamWaitEvent(f->stream, grp[d->left]->dist->ev_copied, 0));
-        CUDA_TRY(cudaStreamWaitEvent(f->stream, grp[d->right]->dist->ev_copied, 0));
-    }
     CUDA_TRY(cudaMemsetAsync(f->s.sendL, 0, sizeof(XHdr), f->stream));
     CUDA_TRY(cudaMemsetAsync(f->s.sendR, 0, sizeof(XHdr), f->stream));
     StepArgs a;
-    a.cell_lo = 0; a.cell_hi = f->ncell;
     a.step = step; a.use_step_dev = 0; a.seed = seed;
     a.injected = d_inj; a.n_injected = n_inj;
     a.out_base = 0;
@@ -193,40 +199,67 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
         f->prof_events.push_back(e0); f->prof_events.push_back(e1);
         CUDA_TRY(cudaEventRecord(e0, f->stream));
     }
-    launch_step(f->g, f->p, f->s, a, (uint32_t)f->cap, f->stream);
+    const uint32_t dh = (uint32_t)f->g.dh, nown = (uint32_t)f->g.nown;
+    const bool split = nown >= 5 && d->overlap;
+    if (split) {
+        // border: columns {ghost, 1, 2} and {nown-1, nown, ghost, slack} (ghost threads only invalidate their WRITE
+        // slot); the grid covers capx birds per range and the kernel flags ERR_EXCHANGE if a range holds more
+        // (capx is 8x the mean population of two columns)
+        const uint32_t ranges[2][2] = {{0, 3 * dh}, {(nown - 1) * dh, (nown + 3) * dh}};
+        for (int r = 0; r < 2; ++r) {
+            a.cell_lo = ranges[r][0]; a.cell_hi = ranges[r][1];
+            launch_step(f->g, f->p, f->s, a, f->s.capx, f->stream);
+            f->launches += 1;
+        }
+        CUDA_TRY(cudaEventRecord(d->ev_sent, f->stream));
+        a.cell_lo = 3 * dh; a.cell_hi = (nown - 1) * dh;
+        launch_step(f->g, f->p, f->s, a, (uint32_t)f->cap, f->stream);
+        f->launches += 1;
+    } else {
+        a.cell_lo = 0; a.cell_hi = f->ncell;
+        launch_step(f->g, f->p, f->s, a, (uint32_t)f->cap, f->stream);
+        f->launches += 1;
+        CUDA_TRY(cudaEventRecord(d->ev_sent, f->stream));
+    }
     if (prof) CUDA_TRY(cudaEventRecord(f->prof_events.back(), f->stream));
-    f->launches += 1;
     CUDA_TRY(cudaGetLastError());
-    if (d->transport == 1) CUDA_TRY(cudaEventRecord(d->ev_sent, f->stream));
     return FLK_OK;
 }
 
-// phase 2: move the messages
+// phase 2: move the messages (on the comm stream, as soon as the border columns are done)
 static int dist_phase_exchange(flk_field *f) {
     flk_dist_state *d = f->dist;
     const size_t nbytes = xbuf_bytes(f->s.capx);
+    cudaStream_t cs = d->comm_stream;
     if (d->transport == 0) {
+        CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_sent, 0));
         NCCL_TRY(g_nccl.GroupStart());
-        NCCL_TRY(g_nccl.Send(f->s.sendL, nbytes, kNcclUint8, d->left, d->comm, f->stream));
-        NCCL_TRY(g_nccl.Send(f->s.sendR, nbytes, kNcclUint8, d->right, d->comm, f->stream));
+        NCCL_TRY(g_nccl.Send(f->s.sendL, nbytes, kNcclUint8, d->left, d->comm, cs));
+        NCCL_TRY(g_nccl.Send(f->s.sendR, nbytes, kNcclUint8, d->right, d->comm, cs));
         // order matters only for world==2 (both messages come from the same peer): its sendL is my recvR
-        NCCL_TRY(g_nccl.Recv(f->s.recvR, nbytes, kNcclUint8, d->right, d->comm, f->stream));
-        NCCL_TRY(g_nccl.Recv(f->s.recvL, nbytes, kNcclUint8, d->left, d->comm, f->stream));
+        NCCL_TRY(g_nccl.Recv(f->s.recvR, nbytes, kNcclUint8, d->right, d->comm, cs));
+        NCCL_TRY(g_nccl.Recv(f->s.recvL, nbytes, kNcclUint8, d->left, d->comm, cs));
         NCCL_TRY(g_nccl.GroupEnd());
     } else {
         flk_field *L = d->group[d->left], *R = d->group[d->right];
-        CUDA_TRY(cudaStreamWaitEvent(f->stream, L->dist->ev_sent, 0));
-        CUDA_TRY(cudaStreamWaitEvent(f->stream, R->dist->ev_sent, 0));
-        CUDA_TRY(cudaMemcpyPeerAsync(f->s.recvL, f->device, L->s.sendR, L->device, nbytes, f->stream));
-        CUDA_TRY(cudaMemcpyPeerAsync(f->s.recvR, f->device, R->s.sendL, R->device, nbytes, f->stream));
-        CUDA_TRY(cudaEventRecord(d->ev_copied, f->stream));
-        d->copied_valid = true;
+        CUDA_TRY(cudaStreamWaitEvent(cs, L->dist->ev_sent, 0));
+        CUDA_TRY(cudaStreamWaitEvent(cs, R->dist->ev_sent, 0));
+        CUDA_TRY(cudaMemcpyPeerAsync(f->s.recvL, f->device, L->s.sendR, L->device, nbytes, cs));
+        CUDA_TRY(cudaMemcpyPeerAsync(f->s.recvR, f->device, R->s.sendL, R->device, nbytes, cs));
     }
+    CUDA_TRY(cudaEventRecord(d->ev_copied, cs));
     return FLK_OK;
 }
 
 // phase 3: arrivals join the WRITE buffer, then lazy_update
 static int dist_phase_finish(flk_field *f) {
+    flk_dist_state *d = f->dist;
+    CUDA_TRY(cudaStreamWaitEvent(f->stream, d->ev_copied, 0));
+    if (d->transport == 1) {
+        // LOCAL: my neighbours read MY send buffers with their own copies; the next tick may not clear them before
+        CUDA_TRY(cudaStreamWaitEvent(f->stream, d->group[d->left]->dist->ev_copied, 0));
+        CUDA_TRY(cudaStreamWaitEvent(f->stream, d->group[d->right]->dist->ev_copied, 0));
+    }
     launch_unpack(f->g, f->s, f->stream);
     f->launches += 1;
     CUDA_TRY(cudaGetLastError());

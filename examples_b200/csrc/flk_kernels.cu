@@ -307,10 +307,14 @@ __device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, cons
 }
 
 // interior accumulation out of the CTA's shared-memory tile (same order, same arithmetic as accumulate_interior)
+#ifndef FLK_SMEM_UNROLL
+#define FLK_SMEM_UNROLL 2
+#endif
+constexpr int kSmemUnroll = FLK_SMEM_UNROLL;
 template <int MATH>
 __device__ __forceinline__ void accumulate_run_smem(const float4 *tile, uint32_t j, uint32_t e, float mx_, float my_,
                                                     float &xa, float &ya, float &xc, float &yc, float &xs, float &ys) {
-#pragma unroll 2
+#pragma unroll kSmemUnroll
     for (; j < e; ++j) {
         const float4 o = tile[j];
         const float dx = __fadd_rn(mx_, -o.x);                              // bird.rs:54 (no seam in reach)
@@ -337,8 +341,11 @@ __device__ __forceinline__ void accumulate_run_smem(const float4 *tile, uint32_t
 
 // k_step: one thread per READ bird.  TILE = stage the CTA's three window-column runs in shared memory with TMA bulk
 // copies when the CTA's birds sit in one interior column (the common case); other CTAs read through L1.
+#ifndef FLK_STEP_MINBLOCKS
+#define FLK_STEP_MINBLOCKS 12
+#endif
 template <bool RELAX, int MATH, bool TILE>
-__global__ void __launch_bounds__(128, 12) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
+__global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
     __shared__ __align__(128) float4 tile[TILE ? 3 : 1][TILE ? TILE_CAP : 1];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int shc[5];
@@ -346,6 +353,8 @@ __global__ void __launch_bounds__(128, 12) k_step(const Geom g, const Params p, 
     const uint32_t lo = __ldg(s.cell_start + a.cell_lo);
     const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
     const uint32_t first = lo + blockIdx.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && hi - lo > gridDim.x * blockDim.x)
+        atomicOr(s.err_flag, ERR_EXCHANGE);        // the launch does not cover the range (border launches use capx)
     if (first >= hi) return;                       // whole CTA out of range
     const uint32_t i = first + threadIdx.x;
     const bool valid = i < hi;
