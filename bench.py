@@ -132,12 +132,15 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes per k_step launch from the committed ncu capture, if one exists for this workload."""
+def ncu_traffic_per_launch(birds_per_launch: int):
+    """DRAM bytes of one k_step launch from the committed ncu --set full capture (profiles/), or None when the
+    capture was taken on a different launch size."""
     p = os.path.join(ROOT, "profiles", "k_step_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p))
+            d = json.load(open(p))
+            if int(d["birds_per_launch"]) == int(birds_per_launch):
+                return float(d["bytes_per_launch"])
         except Exception:
             return None
     return None
@@ -283,7 +286,7 @@ def run_ours(args, world: int, rank: int, local_rank: int):
     k_avg_ms = max_over_ranks(k_ms / max(k_n, 1))
     peak, peak_src = measured_peak_gbs()
     achieved = ALGO_BYTES_PER_UPDATE * n_local / (k_avg_ms * 1e-3) / 1e9
-    traffic = ncu_traffic_per_launch()
+    traffic = ncu_traffic_per_launch(n_total // world)
 
     # ---- e2e: per step, host -> device copy of every agent, one tick, device -> host read of the new state ----
     e2e_steps = max(1, min(args.e2e_steps, args.steps))

@@ -121,7 +121,6 @@ int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc,
     f->launches += 1;
     CUDA_TRY(cudaGetLastError());
     f->w_count += n;
-    f->graph_valid = false;
     return FLK_OK;
 }
 
@@ -308,7 +307,9 @@ int flk_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed) 
     if (f->g.mode == 1) return dist_run(f, first_step, n_steps, seed);
     if (f->w_count != 0) return fail(FLK_E_STATE, "flk_run needs an empty WRITE buffer (call flk_lazy_update first)");
     CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
-    if (f->profile || !f->use_graph) {
+    // a captured tick pays off from a handful of replays on; short runs without a cached graph launch directly
+    const bool have_graph = f->graph_valid && f->graph_n == f->n_read && f->graph_seed == seed;
+    if (f->profile || !f->use_graph || (!have_graph && n_steps < 8)) {
         for (uint64_t t = 0; t < n_steps; ++t) {
             rc = enqueue_step(f, first_step + t, 0, seed, nullptr, 0);
             if (rc) return rc;
