@@ -290,9 +290,10 @@ def run_ours(args, world: int, rank: int, local_rank: int):
 
     # ---- e2e: per step, host -> device copy of every agent, one tick, device -> host read of the new state ----
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
-    o_id = torch.empty_like(h_id)
-    o_loc = torch.empty_like(h_loc)
-    o_ld = torch.empty_like(h_ld)
+    o_id = torch.empty_like(h_id).pin_memory()      # empty_like of a pinned tensor is pageable: pin explicitly
+    o_loc = torch.empty_like(h_loc).pin_memory()
+    o_ld = torch.empty_like(h_ld).pin_memory()
+    assert o_id.is_pinned() and o_loc.is_pinned() and o_ld.is_pinned() and h_id.is_pinned() and h_loc.is_pinned()
     ids_np = None
     for it in range(e2e_steps + 1):
         if it == 1:
