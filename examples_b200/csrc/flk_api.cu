@@ -129,7 +129,7 @@ int enqueue_lazy_update(flk_field *f, int bump_step) {
     launch_scan(f->s, m, f->stream);
     launch_scatter(f->s, (uint32_t)f->w_count, f->g.mode == 1, f->stream);
     launch_rank(f->s, (uint32_t)f->w_count, f->ncell, bump_step, f->stream);
-    f->launches += 3 + (f->w_count ? 1 : 0) + 1;
+    f->launches += 3 + (f->g.mode == 1 ? 2 : (f->w_count ? 1 : 0)) + 1;
     CUDA_TRY(cudaGetLastError());
     f->n_read = f->w_count;  // single GPU: every WRITE entry is kept
     f->w_count = 0;

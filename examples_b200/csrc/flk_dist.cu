@@ -86,6 +86,13 @@ struct flk_dist_state {
     cudaStream_t comm_stream = nullptr;   // high-priority stream the exchange runs on, beside the interior step
     cudaEvent_t ev_sent = nullptr;     // my send buffers are complete (border columns stepped)
     cudaEvent_t ev_copied = nullptr;   // the exchange is complete: neighbours' messages are in my recv buffers
+    // host-side upper bound of the READ population (grid sizing): the device count is copied back asynchronously
+    // every tick and used once it has landed, so no tick ever waits for it
+    uint32_t *h_count = nullptr;       // pinned
+    cudaEvent_t ev_count = nullptr;
+    bool count_pending = false;
+    uint64_t known = 0, known_tick = 0, copy_tick = 0, tick_no = 0;   // tick_no = ticks enqueued so far
+    bool have_known = false;
     bool overlap = true;               // FLK_DIST_OVERLAP=0 steps all columns before the exchange (A/B measurements)
     bool committed = false;
 };
@@ -98,6 +105,8 @@ void dist_free(flk_field *f) {
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
     if (d->xbuf) cudaFree(d->xbuf);
     if (d->comm_stream) cudaStreamDestroy(d->comm_stream);
+    if (d->h_count) cudaFreeHost(d->h_count);
+    if (d->ev_count) cudaEventDestroy(d->ev_count);
     if (d->ev_sent) cudaEventDestroy(d->ev_sent);
     if (d->ev_copied) cudaEventDestroy(d->ev_copied);
     if (d->rank == 0 && d->group) delete[] d->group;
@@ -165,6 +174,8 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
         cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
         e = cudaStreamCreateWithPriority(&d->comm_stream, cudaStreamNonBlocking, hi_p);
     }
+    if (e == cudaSuccess) e = cudaHostAlloc(&d->h_count, 4, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_count, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_sent, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -175,6 +186,21 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     f->n_read = 0;
     *out = f;
     return FLK_OK;
+}
+
+// upper bound of the READ population for grid sizing: the last count that has landed on the host plus what the
+// exchanges enqueued since then can have added (2*capx per tick), never above the capacity
+static uint32_t read_upper_bound(flk_field *f) {
+    flk_dist_state *d = f->dist;
+    if (d->count_pending && cudaEventQuery(d->ev_count) == cudaSuccess) {
+        d->known = *d->h_count;          // population after tick `copy_tick`
+        d->known_tick = d->copy_tick;
+        d->have_known = true;
+        d->count_pending = false;
+    }
+    if (!d->have_known) return (uint32_t)f->cap;
+    const uint64_t b = d->known + (d->tick_no - d->known_tick) * 2ull * f->s.capx;
+    return (uint32_t)(b < f->cap ? b : f->cap);
 }
 
 // phase 1 of a tick on one strip: clear the outgoing messages, step (or re-stage) every owned bird.
@@ -213,11 +239,11 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
         }
         CUDA_TRY(cudaEventRecord(d->ev_sent, f->stream));
         a.cell_lo = 3 * dh; a.cell_hi = (nown - 1) * dh;
-        launch_step(f->g, f->p, f->s, a, (uint32_t)f->cap, f->stream);
+        launch_step(f->g, f->p, f->s, a, read_upper_bound(f), f->stream);
         f->launches += 1;
     } else {
         a.cell_lo = 0; a.cell_hi = f->ncell;
-        launch_step(f->g, f->p, f->s, a, (uint32_t)f->cap, f->stream);
+        launch_step(f->g, f->p, f->s, a, read_upper_bound(f), f->stream);
         f->launches += 1;
         CUDA_TRY(cudaEventRecord(d->ev_sent, f->stream));
     }
@@ -231,8 +257,10 @@ static int dist_phase_exchange(flk_field *f) {
     flk_dist_state *d = f->dist;
     const size_t nbytes = xbuf_bytes(f->s.capx);
     cudaStream_t cs = d->comm_stream;
+    // my own border step of THIS tick is behind my unpack/scatter of the previous tick on the main stream, so waiting
+    // for it also protects the receive buffers the previous tick may still be reading
+    CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_sent, 0));
     if (d->transport == 0) {
-        CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_sent, 0));
         NCCL_TRY(g_nccl.GroupStart());
         NCCL_TRY(g_nccl.Send(f->s.sendL, nbytes, kNcclUint8, d->left, d->comm, cs));
         NCCL_TRY(g_nccl.Send(f->s.sendR, nbytes, kNcclUint8, d->right, d->comm, cs));
@@ -263,11 +291,22 @@ static int dist_phase_finish(flk_field *f) {
     launch_unpack(f->g, f->s, f->stream);
     f->launches += 1;
     CUDA_TRY(cudaGetLastError());
-    f->w_count = f->cap;  // grid bound only; validity is decided on the device
+    // grid bounds only; validity is decided on the device.  The new READ population is at most the old bound plus
+    // both messages.
+    const uint64_t ub = (uint64_t)read_upper_bound(f) + 2ull * f->s.capx;
+    f->w_count = ub < f->cap ? ub : f->cap;
     int rc = enqueue_lazy_update(f, 0);
-    f->n_read = f->cap;   // upper bound (exact count lives on the device)
+    f->n_read = f->cap;   // the host only keeps an upper bound (the exact count lives on the device)
     f->w_count = 0;
-    return rc;
+    if (rc) return rc;
+    d->tick_no += 1;
+    if (!d->count_pending) {
+        CUDA_TRY(cudaMemcpyAsync(d->h_count, f->s.n_read_dev, 4, cudaMemcpyDeviceToHost, f->stream));
+        CUDA_TRY(cudaEventRecord(d->ev_count, f->stream));
+        d->count_pending = true;
+        d->copy_tick = d->tick_no;
+    }
+    return FLK_OK;
 }
 
 static int dist_tick(flk_field *f, uint64_t step, uint64_t seed, const float2 *d_inj, uint32_t n_inj, int identity) {
@@ -295,6 +334,7 @@ static int dist_publish_uploads(flk_field *f) {
 
 int dist_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld) {
     f->dist->committed = false;
+    f->dist->have_known = false;   // the population is about to change outside the tick loop
     return write_append(f, n, id, loc, ld);
 }
 

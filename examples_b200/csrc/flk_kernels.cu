@@ -625,8 +625,8 @@ void launch_scan(const Store &s, uint32_t m, cudaStream_t st) {
 // k_scatter / k_rank: WRITE buffer -> READ buffer in (cell, ascending id) order
 // ------------------------------------------------------------------------------------------------
 template <bool DIST>
-__global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n, uint32_t base) {
+    const uint32_t i = base + blockIdx.x * blockDim.x + threadIdx.x;
     if (DIST) {
         // valid WRITE slots: [0, n_read) stepped, [cap, cap+countL) and [cap+capx, cap+capx+countR) received
         if (i < s.cap) {
@@ -652,12 +652,14 @@ __global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n) {
 
 void launch_scatter(const Store &s, uint32_t n, int dist, cudaStream_t st) {
     if (dist) {
-        const uint32_t tot = s.cap + 2 * s.capx;
-        k_scatter<true><<<(tot + 255) / 256, 256, 0, st>>>(s, tot);
+        // stepped slots [0, n) (n = host upper bound of the READ population), then the two receive regions
+        const uint32_t nn = n < s.cap ? n : s.cap;
+        if (nn) k_scatter<true><<<(nn + 255) / 256, 256, 0, st>>>(s, nn, 0);
+        k_scatter<true><<<(2 * s.capx + 255) / 256, 256, 0, st>>>(s, 2 * s.capx, s.cap);
         return;
     }
     if (n == 0) return;
-    k_scatter<false><<<(n + 255) / 256, 256, 0, st>>>(s, n);
+    k_scatter<false><<<(n + 255) / 256, 256, 0, st>>>(s, n, 0);
 }
 
 __global__ void __launch_bounds__(256) k_rank(const Store s, uint32_t ncell, int bump_step) {
