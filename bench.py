@@ -352,15 +352,15 @@ def run_ours(args, world: int, rank: int, local_rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="weak16m", choices=["weak16m", "strong16m", "1m", "clustered"])
     ap.add_argument("--birds-per-gpu", type=int, default=None)
     ap.add_argument("--math", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-birds", type=int, default=1_000_000)
-    ap.add_argument("--cpu-ticks", type=int, default=10)
+    ap.add_argument("--cpu-birds", type=int, default=1_000_000)   # birds of the CPU sample (per tick)
+    ap.add_argument("--cpu-ticks", type=int, default=200)        # ~10 s of CPU work on 16 cores
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

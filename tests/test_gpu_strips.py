@@ -87,6 +87,19 @@ def test_strips_clustered_heavy_migration():
         assert bits_equal(from_arrays(*g.snapshot_by_id()), from_arrays(*f.snapshot_by_id())), t0
 
 
+@pytest.mark.parametrize("n", [2, 5, 8])
+def test_strips_long_unsynchronised_runs(n):
+    """100 ticks enqueued back to back (no host synchronisation in between): exercises the event ordering between the
+    main and the comm stream of every strip (send/receive buffer reuse across ticks)"""
+    W = 400.0
+    birds = uniform_birds(16000, W, W)
+    f, g = single(birds, W, W), group(birds, W, W, n)
+    for rep in range(3):
+        f.run(100 * rep, 100)
+        g.run(100 * rep, 100)
+        assert bits_equal(from_arrays(*g.snapshot_by_id()), from_arrays(*f.snapshot_by_id())), (n, rep)
+
+
 def test_strips_slack_column_and_seam():
     """a bird landing exactly on x == W (slack column, owned by the strip holding column 0) and birds crossing
     the seam between the last and the first strip"""
