@@ -38,6 +38,7 @@ SIGNATURES = {
     "flk_num_objects": [_vp, _P(_u64)],
     "flk_snapshot": [_vp, _vp, _vp, _vp, _P(_u64)],
     "flk_get_binning": [_vp, _vp, _vp],
+    "flk_get_object": [_vp, _u32, _P(_f32), _P(_i32)],
     "flk_synchronize": [_vp],
     "flk_elapsed_ms": [_vp, _P(_f32)],
     "flk_stream": [_vp, _P(_vp)],

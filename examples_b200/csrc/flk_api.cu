@@ -42,7 +42,7 @@ int field_alloc(flk_field *f) {
     CUDA_TRY(cudaMalloc(&s.tslot, capw * 4));
     CUDA_TRY(cudaMalloc(&s.cnt, m * 4));
     // one scratch block: the ranking stage (16 B/bird) during lazy_update; upload / snapshot staging otherwise
-    CUDA_TRY(cudaMalloc(&f->scratch, cap * 20 + 64));
+    CUDA_TRY(cudaMalloc(&f->scratch, cap * 20 + 128));
     s.stage = reinterpret_cast<uint4 *>(f->scratch);
     const uint64_t nblk = (m + 2047) / 2048 + 1;
     CUDA_TRY(cudaMalloc(&s.blocksum, nblk * 4));
@@ -367,6 +367,26 @@ int flk_snapshot(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t
         if (last_d) CUDA_TRY(cudaMemcpyAsync(last_d, d_ld, nr * 8, cudaMemcpyDeviceToHost, f->stream));
     }
     CUDA_TRY(cudaStreamSynchronize(f->stream));
+    return FLK_OK;
+}
+
+int flk_get_object(flk_field *f, uint32_t id, float out[4], int32_t *found) {
+    CHECK_HANDLE(f);
+    if (!out || !found) return fail(FLK_E_INVALID, "null argument");
+    *found = 0;
+    // result slot at the tail of the scratch block (free outside lazy_update; stream order protects it)
+    float4 *d_out = reinterpret_cast<float4 *>(f->scratch + ((f->cap * 20 + 15) & ~(uint64_t)15));
+    uint32_t *d_found = reinterpret_cast<uint32_t *>(d_out + 1);
+    CUDA_TRY(cudaMemsetAsync(d_out, 0, 32, f->stream));
+    launch_find(f->s, (uint32_t)f->n_read, id, d_out, d_found, f->stream);
+    f->launches += f->n_read ? 1 : 0;
+    CUDA_TRY(cudaGetLastError());
+    float h[8];
+    CUDA_TRY(cudaMemcpyAsync(h, d_out, 32, cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    uint32_t cnt;
+    memcpy(&cnt, &h[4], 4);
+    if (cnt) { memcpy(out, h, 16); *found = 1; }
     return FLK_OK;
 }
 

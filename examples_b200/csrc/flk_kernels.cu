@@ -737,6 +737,21 @@ void launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Field2D::get / get_location: look one id up in the READ buffer
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_find(const Store s, uint32_t id, float4 *out, uint32_t *found) {
+    const uint32_t n = *s.n_read_dev;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || s.ids[i] != id) return;
+    if (atomicAdd(found, 1u) == 0) *out = reinterpret_cast<const float4 *>(s.rec)[i];
+}
+
+void launch_find(const Store &s, uint32_t n_upper, uint32_t id, float4 *out, uint32_t *found, cudaStream_t st) {
+    if (n_upper == 0) return;
+    k_find<<<(n_upper + 255) / 256, 256, 0, st>>>(s, id, out, found);
+}
+
+// ------------------------------------------------------------------------------------------------
 // snapshot helper: split READ records into loc / last_d arrays
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_split(const Store s, uint32_t n, float2 *loc, float2 *ld) {

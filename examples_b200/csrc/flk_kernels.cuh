@@ -63,6 +63,7 @@ void launch_scatter(const Store &s, uint32_t n_write_extent, int dist, cudaStrea
 void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st);
 void launch_selftest_div2(uint64_t n, uint64_t seed, unsigned long long *mismatches, cudaStream_t st);
 void launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t st);
+void launch_find(const Store &s, uint32_t n_upper, uint32_t id, float4 *out, uint32_t *found, cudaStream_t st);
 void launch_split(const Store &s, uint32_t n, float2 *loc, float2 *ld, cudaStream_t st);
 void launch_query_count(const Geom &g, const Store &s, uint32_t nq, const float2 *loc, float dist, int relax,
                         uint32_t *counts, cudaStream_t st);

@@ -206,3 +206,51 @@ class MgpuGroup:
         ld = np.concatenate([p[2] for p in parts])
         o = np.argsort(ids, kind="stable")
         return ids[o], loc[o], ld[o]
+
+
+class DistFlocker:
+    """flockers_mpi/src/model/state.rs:21-190 with field1 on this rank's GPU strip.
+
+    `before_step` (ghosts), every owned `Bird::step`, `after_step` (migration) and `update` (lazy_update) are ONE
+    collective call, `field1.step`; the State hooks are kept so that a Schedule written against the reference
+    still drives it."""
+
+    def __init__(self, dim, initial_flockers: int, device: int, rank: int, world: int, capacity: int | None = None,
+                 init_seed: int = 0xF10C, step_seed: int = 0xB12D):
+        self.step = 0
+        self.dim = dim
+        self.initial_flockers = initial_flockers
+        self.rank, self.world = rank, world
+        self.init_seed, self.step_seed = init_seed, step_seed
+        cap = capacity or max(2 * initial_flockers // world + 1024, 1024)
+        self.field1 = DistField2D(dim[0], dim[1], DISCRETIZATION, capacity=cap, device=device, rank=rank, world=world)
+
+    def init(self, schedule=None):
+        """state.rs:51-103: rank 0's placement; here every rank draws the same placement and keeps what it owns
+        (flk_set_objects on a strip handle drops birds of other strips), which needs no MPI scatter."""
+        rng = np.random.Generator(np.random.Philox(self.init_seed))
+        r = rng.random((self.initial_flockers, 2), dtype=np.float32)
+        loc = r * np.array(self.dim, dtype=np.float32)
+        ids = np.arange(self.initial_flockers, dtype=np.uint32)
+        col = column_of(loc[:, 0], DISCRETIZATION)
+        c0, c1 = self.field1.strip()
+        mine = (col >= c0) & (col < c1)
+        if c0 == 0:
+            mine |= col >= self.field1.mx
+        self.field1.set_objects(ids[mine], loc[mine], np.zeros_like(loc[mine]))
+        self.field1.commit()
+
+    def before_step(self, schedule=None):   # state.rs:113-133, folded into field1.step
+        pass
+
+    def after_step(self, schedule=None):    # state.rs:139-175, folded into field1.step
+        pass
+
+    def update(self, step: int):            # state.rs:105-107, folded into field1.step
+        self.step = step
+
+    def tick(self):
+        self.before_step()
+        self.field1.step(self.step, self.step_seed)
+        self.after_step()
+        self.update(self.step + 1)

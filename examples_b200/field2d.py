@@ -176,6 +176,20 @@ class Field2D:
             check(rc)
             return offsets, ids[: int(offsets[nq])]
 
+    def get(self, bird_id: int) -> Bird | None:
+        """Field2D::get(&object): the stored copy of the object with this id, or None"""
+        out = (C.c_float * 4)()
+        found = C.c_int32()
+        check(self._L.flk_get_object(self._h, bird_id, out, C.byref(found)))
+        if not found.value:
+            return None
+        return Bird(bird_id, Real2D(out[0], out[1]), Real2D(out[2], out[3]))
+
+    def get_location(self, bird_id: int) -> Real2D | None:
+        """Field2D::get_location(object) (flockers/src/visualization/bird_vis.rs:23)"""
+        b = self.get(bird_id)
+        return None if b is None else b.loc
+
     def num_objects(self) -> int:
         n = C.c_uint64()
         check(self._L.flk_num_objects(self._h, C.byref(n)))

@@ -115,6 +115,11 @@ int flk_num_objects(const flk_field *f, uint64_t *n);
  * copies the READ buffer, in (cell, id) order, to HOST arrays (any of them may be NULL). Synchronous. */
 int flk_snapshot(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n);
 
+/* Field2D::get(&object) / Field2D::get_location(object)   flockers/src/visualization/vis_state.rs:52, bird_vis.rs:23
+ * Looks one object up by id in the READ buffer (the reference hashes Bird by id, bird.rs:148-163).  Synchronous.
+ * *found = 0 when no object has that id (the reference returns None); out = {x, y, last_d.x, last_d.y}. */
+int flk_get_object(flk_field *f, uint32_t id, float out[4], int32_t *found);
+
 /* the binning itself: cell_start[dw*dh+1] (flat cell = cx*dh+cy) and ids in sorted order */
 int flk_get_binning(flk_field *f, uint32_t *cell_start, uint32_t *sorted_ids);
 

@@ -32,6 +32,7 @@ extern "C" {
                            offsets: *mut u64, ids: *mut u32, cap: u64) -> c_int;
     pub fn flk_num_objects(f: *const flk_field, n: *mut u64) -> c_int;
     pub fn flk_snapshot(f: *mut flk_field, id: *mut u32, loc: *mut c_float, last_d: *mut c_float, n: *mut u64) -> c_int;
+    pub fn flk_get_object(f: *mut flk_field, id: u32, out: *mut c_float, found: *mut i32) -> c_int;
     pub fn flk_get_binning(f: *mut flk_field, cell_start: *mut u32, sorted_ids: *mut u32) -> c_int;
     pub fn flk_synchronize(f: *mut flk_field) -> c_int;
     pub fn flk_elapsed_ms(f: *mut flk_field, ms: *mut c_float) -> c_int;

@@ -78,6 +78,25 @@ def main():
         print(f"[nccl x{world}] owned total {int(owned.item())}", flush=True)
         ok &= int(owned.item()) == n
     f.close()
+    # 3. the flockers_mpi model as shipped (flockers_mpi/src/main.rs:38-44: 1000 birds, 100x100, 100 steps) through the
+    #    State-shaped mirror, against the single-GPU Flocker with the same placement
+    from examples_b200 import Flocker, Schedule
+    from examples_b200.distributed import DistFlocker
+    st = DistFlocker((100.0, 100.0), 1000, device=local, rank=rank, world=world)
+    st.init()
+    for _ in range(100):
+        st.tick()
+    got = gather(st.field1)
+    if rank == 0:
+        ref = Flocker((100.0, 100.0), 1000, device=local)
+        sch = Schedule()
+        ref.init(sch)
+        for _ in range(100):
+            sch.step(ref)
+        same = bits_equal(got, from_arrays(*ref.field1.snapshot_by_id()))
+        print(f"[nccl x{world}] flockers_mpi shipped config, 100 steps vs flockers: {'ok' if same else 'MISMATCH'}", flush=True)
+        ok &= same
+    st.field1.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()

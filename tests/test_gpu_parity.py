@@ -134,6 +134,21 @@ def test_single_query_api_and_capacity_code():
     assert rc == _lib.E_CAPACITY and n.value == len(want) and np.array_equal(ids, want[:4])
 
 
+def test_get_and_get_location_by_id():
+    """Field2D::get / get_location (visualization accessors): lookup by id in the READ buffer"""
+    birds = uniform_birds(1000, 100.0, 100.0)
+    f = load_gpu(birds, 100.0, 100.0)
+    f.run(0, 3)
+    ids, loc, ld = f.snapshot_by_id()
+    for i in (0, 17, 999):
+        b = f.get(i)
+        assert b is not None and b.id == i
+        assert (np.float32(b.loc.x), np.float32(b.loc.y)) == (loc[i, 0], loc[i, 1])
+        assert (np.float32(b.last_d.x), np.float32(b.last_d.y)) == (ld[i, 0], ld[i, 1])
+        assert f.get_location(i).x == b.loc.x
+    assert f.get(5000) is None and f.get_location(123456) is None
+
+
 # ---- Bird::step ------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("maker,n,W", [(uniform_birds, 1000, 100.0), (clustered_birds, 4000, 200.0)])
