@@ -122,13 +122,16 @@ __device__ __forceinline__ void accumulate_window(const Geom &g, const Params &p
 
 // Interior form (k == 1, no wrap, no seam): the three column runs are known without any modulo or branching, all six
 // cell_start loads are issued up front, and each run is a tight 2x-unrolled loop of 25 instructions per candidate.
-// The middle run is split at the bird's own index (bird.rs:53).  Exact arithmetic, see div2_rn_interior.
-template <int MATH>
-__device__ __forceinline__ void accumulate_run(const float4 *__restrict__ rec, uint32_t j, uint32_t e, float mx_, float my_,
-                                               float &xa, float &ya, float &xc, float &yc, float &xs, float &ys) {
+// The bird itself sits in the middle run and is neutralised there (bird.rs:53, see accumulate_run_smem).  Exact
+// arithmetic, see div2_rn_interior.
+template <int MATH, bool SELF>
+__device__ __forceinline__ void accumulate_run(const float4 *__restrict__ rec, uint32_t j, uint32_t e, uint32_t self,
+                                               float mx_, float my_, float &xa, float &ya, float &xc, float &yc,
+                                               float &xs, float &ys) {
 #pragma unroll 2
     for (; j < e; ++j) {
-        const float4 o = __ldg(rec + j);
+        float4 o = __ldg(rec + j);
+        if (SELF && j == self) { o.z = 0.0f; o.w = 0.0f; }   // see accumulate_run_smem
         const float dx = __fadd_rn(mx_, -o.x);                              // bird.rs:54 (no seam in reach)
         const float dy = __fadd_rn(my_, -o.y);                              // :55
         const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));   // :59
@@ -160,10 +163,9 @@ __device__ __forceinline__ void accumulate_interior(const Geom &g, const Store &
     const uint32_t a1 = __ldg(cs + g.dh), b1 = __ldg(cs + g.dh + 3);
     const uint32_t a2 = __ldg(cs + 2 * g.dh), b2 = __ldg(cs + 2 * g.dh + 3);
     float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
-    accumulate_run<MATH>(rec, a0, b0, me.x, me.y, xa, ya, xc, yc, xs, ys);
-    accumulate_run<MATH>(rec, a1, i, me.x, me.y, xa, ya, xc, yc, xs, ys);       // own cell is in the middle run
-    accumulate_run<MATH>(rec, i + 1, b1, me.x, me.y, xa, ya, xc, yc, xs, ys);
-    accumulate_run<MATH>(rec, a2, b2, me.x, me.y, xa, ya, xc, yc, xs, ys);
+    accumulate_run<MATH, false>(rec, a0, b0, 0, me.x, me.y, xa, ya, xc, yc, xs, ys);
+    accumulate_run<MATH, true>(rec, a1, b1, i, me.x, me.y, xa, ya, xc, yc, xs, ys);   // own cell is in the middle run
+    accumulate_run<MATH, false>(rec, a2, b2, 0, me.x, me.y, xa, ya, xc, yc, xs, ys);
     acc.xa = xa; acc.ya = ya; acc.xc = xc; acc.yc = yc; acc.xs = xs; acc.ys = ys;
     acc.nvec = (b0 - a0) + (b1 - a1) + (b2 - a2);
     acc.count = (int)acc.nvec - 1;
@@ -311,12 +313,17 @@ __device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, cons
 #define FLK_SMEM_UNROLL 2
 #endif
 constexpr int kSmemUnroll = FLK_SMEM_UNROLL;
-template <int MATH>
-__device__ __forceinline__ void accumulate_run_smem(const float4 *tile, uint32_t j, uint32_t e, float mx_, float my_,
-                                                    float &xa, float &ya, float &xc, float &yc, float &xs, float &ys) {
+// SELF: the run contains the bird itself at index `self` (bird.rs:53 skips it by id).  Its own record contributes
+// exactly nothing to the avoidance and cohesion sums (dx = dy = +0, 0/den = +0, and an accumulator that started at +0
+// is unchanged by adding +0), so only the consistency terms need a select — cheaper than splitting the run in two.
+template <int MATH, bool SELF>
+__device__ __forceinline__ void accumulate_run_smem(const float4 *tile, uint32_t j, uint32_t e, uint32_t self, float mx_,
+                                                    float my_, float &xa, float &ya, float &xc, float &yc, float &xs,
+                                                    float &ys) {
 #pragma unroll kSmemUnroll
     for (; j < e; ++j) {
-        const float4 o = tile[j];
+        float4 o = tile[j];
+        if (SELF && j == self) { o.z = 0.0f; o.w = 0.0f; }
         const float dx = __fadd_rn(mx_, -o.x);                              // bird.rs:54 (no seam in reach)
         const float dy = __fadd_rn(my_, -o.y);                              // :55
         const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));   // :59
@@ -428,10 +435,9 @@ __global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS) k_step(const Geom g, 
         const uint32_t a1 = __ldg(cs + g.dh), b1 = __ldg(cs + g.dh + 3);
         const uint32_t a2 = __ldg(cs + 2 * g.dh), b2 = __ldg(cs + 2 * g.dh + 3);
         float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
-        accumulate_run_smem<MATH>(tile[0], a0 - sA0, b0 - sA0, me.x, me.y, xa, ya, xc, yc, xs, ys);
-        accumulate_run_smem<MATH>(tile[1], a1 - sA1, i - sA1, me.x, me.y, xa, ya, xc, yc, xs, ys);   // split at self
-        accumulate_run_smem<MATH>(tile[1], i + 1 - sA1, b1 - sA1, me.x, me.y, xa, ya, xc, yc, xs, ys);
-        accumulate_run_smem<MATH>(tile[2], a2 - sA2, b2 - sA2, me.x, me.y, xa, ya, xc, yc, xs, ys);
+        accumulate_run_smem<MATH, false>(tile[0], a0 - sA0, b0 - sA0, 0, me.x, me.y, xa, ya, xc, yc, xs, ys);
+        accumulate_run_smem<MATH, true>(tile[1], a1 - sA1, b1 - sA1, i - sA1, me.x, me.y, xa, ya, xc, yc, xs, ys);
+        accumulate_run_smem<MATH, false>(tile[2], a2 - sA2, b2 - sA2, 0, me.x, me.y, xa, ya, xc, yc, xs, ys);
         acc.xa = xa; acc.ya = ya; acc.xc = xc; acc.yc = yc; acc.xs = xs; acc.ys = ys;
         acc.nvec = (b0 - a0) + (b1 - a1) + (b2 - a2);
         acc.count = (int)acc.nvec - 1;
