@@ -277,6 +277,7 @@ def run_ours(args, world: int, rank: int, local_rank: int):
     ms = max_over_ranks(f.elapsed_ms())
     clocks = sampler.stop() if rank == 0 else None
     k_ms, k_n = f.profile_step_kernel()
+    rebin_ms = f.profile_rebin()
     f.profile_enable(False)
     launches = f.launch_count() - launches0
     n_now = sum_over_ranks(float(f.num_owned()))
@@ -334,6 +335,7 @@ def run_ours(args, world: int, rank: int, local_rank: int):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_step", "kernel_ms": k_avg_ms,
                          "kernel_share_of_step": k_avg_ms / (ms / args.steps), "peak_source": peak_src,
+                         "other_kernels_ms": {"k_scan_x3": rebin_ms[0], "k_scatter": rebin_ms[1], "k_rank": rebin_ms[2]},
                          "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
                          "note": "path is FP32-issue bound, not HBM bound (DESIGN.md roofline)"},
             "cpu_baseline": cpu,

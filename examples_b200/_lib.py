@@ -46,6 +46,7 @@ SIGNATURES = {
     "flk_profile_enable": [_vp, C.c_int],
     "flk_use_graph": [_vp, C.c_int],
     "flk_profile_step_kernel": [_vp, _P(C.c_double), _P(_u64)],
+    "flk_profile_rebin": [_vp, _P(C.c_double), _P(_u64)],
     "flk_host_alloc": [_P(_vp), _u64],
     "flk_host_free": [_vp],
     "flk_selftest_div2": [C.c_int, _u64, _u64, _P(_u64)],

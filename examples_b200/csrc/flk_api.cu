@@ -35,12 +35,13 @@ int field_alloc(flk_field *f) {
     const uint64_t capw = cap + 2ull * s.capx;   // WRITE slots: stepped/uploaded + received from both neighbours
     CUDA_TRY(cudaMalloc(&s.rec, cap * sizeof(Rec)));
     CUDA_TRY(cudaMalloc(&s.ids, cap * 4));
-    CUDA_TRY(cudaMalloc(&s.cell_start, m * 4));
+    const uint64_t mp = ((m + 2047) / 2048) * 2048;   // padded to the scan tile (k_scan_* use whole-tile vector accesses)
+    CUDA_TRY(cudaMalloc(&s.cell_start, mp * 4));
     CUDA_TRY(cudaMalloc(&s.trec, capw * sizeof(Rec)));
     CUDA_TRY(cudaMalloc(&s.tid, capw * 4));
     CUDA_TRY(cudaMalloc(&s.tkey, capw * 4));
     CUDA_TRY(cudaMalloc(&s.tslot, capw * 4));
-    CUDA_TRY(cudaMalloc(&s.cnt, m * 4));
+    CUDA_TRY(cudaMalloc(&s.cnt, mp * 4));
     // one scratch block: the ranking stage (16 B/bird) during lazy_update; upload / snapshot staging otherwise
     CUDA_TRY(cudaMalloc(&f->scratch, cap * 20 + 128));
     s.stage = reinterpret_cast<uint4 *>(f->scratch);
@@ -50,8 +51,8 @@ int field_alloc(flk_field *f) {
     CUDA_TRY(cudaMalloc(&s.n_read_dev, 4));
     CUDA_TRY(cudaMalloc(&s.err_flag, 4));
     CUDA_TRY(cudaMemsetAsync(s.err_flag, 0, 4, f->stream));
-    CUDA_TRY(cudaMemsetAsync(s.cell_start, 0, m * 4, f->stream));
-    CUDA_TRY(cudaMemsetAsync(s.cnt, 0, m * 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(s.cell_start, 0, mp * 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(s.cnt, 0, mp * 4, f->stream));
     CUDA_TRY(cudaMemsetAsync(s.step_dev, 0, 8, f->stream));
     CUDA_TRY(cudaMemsetAsync(s.n_read_dev, 0, 4, f->stream));
     return FLK_OK;
@@ -65,6 +66,7 @@ void field_free(flk_field *f) {
     if (f->d_injected) cudaFree(f->d_injected);
     if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
     for (auto &e : f->prof_events) cudaEventDestroy(e);
+    for (auto &e : f->prof_rebin) cudaEventDestroy(e);
     if (f->ev0) cudaEventDestroy(f->ev0);
     if (f->ev1) cudaEventDestroy(f->ev1);
     if (f->stream) cudaStreamDestroy(f->stream);
@@ -126,9 +128,22 @@ int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc,
 
 int enqueue_lazy_update(flk_field *f, int bump_step) {
     const uint32_t m = f->ncell + 1;
+    const bool prof = f->profile && !f->capturing;
+    auto mark = [&]() -> int {
+        if (!prof) return FLK_OK;
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        f->prof_rebin.push_back(e);
+        CUDA_TRY(cudaEventRecord(e, f->stream));
+        return FLK_OK;
+    };
+    if (int rc = mark()) return rc;
     launch_scan(f->s, m, f->stream);
+    if (int rc = mark()) return rc;
     launch_scatter(f->s, (uint32_t)f->w_count, f->g.mode == 1, f->stream);
+    if (int rc = mark()) return rc;
     launch_rank(f->s, (uint32_t)f->w_count, f->ncell, bump_step, f->stream);
+    if (int rc = mark()) return rc;
     f->launches += 3 + (f->g.mode == 1 ? 2 : (f->w_count ? 1 : 0)) + 1;
     CUDA_TRY(cudaGetLastError());
     f->n_read = f->w_count;  // single GPU: every WRITE entry is kept
@@ -508,6 +523,8 @@ int flk_profile_enable(flk_field *f, int on) {
     CUDA_TRY(cudaStreamSynchronize(f->stream));
     for (auto &e : f->prof_events) cudaEventDestroy(e);
     f->prof_events.clear();
+    for (auto &e : f->prof_rebin) cudaEventDestroy(e);
+    f->prof_rebin.clear();
     f->profile = on != 0;
     return FLK_OK;
 }
@@ -523,6 +540,22 @@ int flk_profile_step_kernel(flk_field *f, double *total_ms, uint64_t *launches) 
     }
     if (total_ms) *total_ms = tot;
     if (launches) *launches = f->prof_events.size() / 2;
+    return FLK_OK;
+}
+
+int flk_profile_rebin(flk_field *f, double ms[3], uint64_t *updates) {
+    CHECK_HANDLE(f);
+    if (!ms) return fail(FLK_E_INVALID, "ms is null");
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    ms[0] = ms[1] = ms[2] = 0.0;
+    uint64_t n = 0;
+    for (size_t i = 0; i + 3 < f->prof_rebin.size(); i += 4, ++n)
+        for (int k = 0; k < 3; ++k) {
+            float t = 0.0f;
+            CUDA_TRY(cudaEventElapsedTime(&t, f->prof_rebin[i + k], f->prof_rebin[i + k + 1]));
+            ms[k] += t;
+        }
+    if (updates) *updates = n;
     return FLK_OK;
 }
 

@@ -573,13 +573,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
     return r;
 }
 
+// cnt / cell_start are allocated padded to a multiple of SCAN_TILE (zero-filled), so whole-tile uint4 accesses are safe
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t *__restrict__ cnt, uint32_t m,
                                                               uint32_t *__restrict__ blocksum) {
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t v = 0;
-#pragma unroll
-    for (int t = 0; t < SCAN_ITEMS; ++t)
-        if (base + t < m) v += cnt[base + t];
+    const uint4 *p = reinterpret_cast<const uint4 *>(cnt + (size_t)blockIdx.x * SCAN_TILE) + threadIdx.x * 2;
+    const uint4 a = p[0], b = p[1];
+    const uint32_t v = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
     uint32_t total;
     block_exclusive_scan<SCAN_THREADS>(v, &total);
     if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
@@ -600,24 +599,18 @@ __global__ void __launch_bounds__(1024) k_scan_spine(uint32_t *__restrict__ bloc
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(uint32_t *__restrict__ cnt, uint32_t m,
                                                             const uint32_t *__restrict__ blocksum,
                                                             uint32_t *__restrict__ cell_start) {
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t item[SCAN_ITEMS];
-    uint32_t v = 0;
-#pragma unroll
-    for (int t = 0; t < SCAN_ITEMS; ++t) {
-        item[t] = (base + t < m) ? cnt[base + t] : 0;
-        v += item[t];
-    }
+    uint4 *pc = reinterpret_cast<uint4 *>(cnt + (size_t)blockIdx.x * SCAN_TILE) + threadIdx.x * 2;
+    uint4 *ps = reinterpret_cast<uint4 *>(cell_start + (size_t)blockIdx.x * SCAN_TILE) + threadIdx.x * 2;
+    const uint4 a = pc[0], b = pc[1];
+    const uint32_t v = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
     uint32_t total;
-    uint32_t run = block_exclusive_scan<SCAN_THREADS>(v, &total) + blocksum[blockIdx.x];
-#pragma unroll
-    for (int t = 0; t < SCAN_ITEMS; ++t) {
-        if (base + t < m) {
-            cell_start[base + t] = run;
-            cnt[base + t] = 0;   // the new WRITE buffer starts empty (lazy_update clears the bags)
-        }
-        run += item[t];
-    }
+    const uint32_t run = block_exclusive_scan<SCAN_THREADS>(v, &total) + blocksum[blockIdx.x];
+    uint4 o0, o1;
+    o0.x = run; o0.y = o0.x + a.x; o0.z = o0.y + a.y; o0.w = o0.z + a.z;
+    o1.x = o0.w + a.w; o1.y = o1.x + b.x; o1.z = o1.y + b.y; o1.w = o1.z + b.z;
+    ps[0] = o0; ps[1] = o1;
+    // the new WRITE buffer starts empty (lazy_update clears the bags)
+    pc[0] = make_uint4(0, 0, 0, 0); pc[1] = make_uint4(0, 0, 0, 0);
 }
 
 void launch_scan(const Store &s, uint32_t m, cudaStream_t st) {

@@ -239,6 +239,14 @@ class Field2D:
     def profile_enable(self, on: bool):
         check(self._L.flk_profile_enable(self._h, int(on)))
 
+    def profile_rebin(self):
+        """(scan_ms, scatter_ms, rank_ms) per lazy_update, averaged over the profiled ones"""
+        ms = (C.c_double * 3)()
+        n = C.c_uint64()
+        check(self._L.flk_profile_rebin(self._h, ms, C.byref(n)))
+        k = max(n.value, 1)
+        return ms[0] / k, ms[1] / k, ms[2] / k
+
     def profile_step_kernel(self):
         ms, n = C.c_double(), C.c_uint64()
         check(self._L.flk_profile_step_kernel(self._h, C.byref(ms), C.byref(n)))

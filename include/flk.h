@@ -136,6 +136,8 @@ int flk_profile_enable(flk_field *f, int on);
 /* flk_run replays a captured CUDA graph per tick (default on); off = plain launches */
 int flk_use_graph(flk_field *f, int on);
 int flk_profile_step_kernel(flk_field *f, double *total_ms, uint64_t *launches);
+/* total device time (ms) of the three lazy_update phases {scan, scatter, rank} and the number of lazy_updates timed */
+int flk_profile_rebin(flk_field *f, double ms[3], uint64_t *updates);
 
 /* pinned host memory helpers (fast flk_set_objects / flk_snapshot) */
 int flk_host_alloc(void **p, uint64_t bytes);

@@ -41,6 +41,7 @@ extern "C" {
     pub fn flk_profile_enable(f: *mut flk_field, on: c_int) -> c_int;
     pub fn flk_use_graph(f: *mut flk_field, on: c_int) -> c_int;
     pub fn flk_profile_step_kernel(f: *mut flk_field, total_ms: *mut c_double, launches: *mut u64) -> c_int;
+    pub fn flk_profile_rebin(f: *mut flk_field, ms: *mut c_double, updates: *mut u64) -> c_int;
     pub fn flk_host_alloc(p: *mut *mut c_void, bytes: u64) -> c_int;
     pub fn flk_host_free(p: *mut c_void) -> c_int;
     pub fn flk_selftest_div2(device: c_int, n: u64, seed: u64, mismatches: *mut u64) -> c_int;
