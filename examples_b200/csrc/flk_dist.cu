@@ -84,6 +84,7 @@ struct flk_dist_state {
     uint8_t *xbuf = nullptr;           // sendL | sendR | recvL | recvR
     flk_field **group = nullptr;       // LOCAL: all handles of the group (owned by rank 0's state)
     cudaStream_t comm_stream = nullptr;   // high-priority stream the exchange runs on, beside the interior step
+    cudaEvent_t ev_tick = nullptr;     // main stream: the previous tick's rebin and this tick's header clears are done
     cudaEvent_t ev_sent = nullptr;     // my send buffers are complete (border columns stepped)
     cudaEvent_t ev_copied = nullptr;   // the exchange is complete: neighbours' messages are in my recv buffers
     // host-side upper bound of the READ population (grid sizing): the device count is copied back asynchronously
@@ -108,6 +109,7 @@ void dist_free(flk_field *f) {
     if (d->h_count) cudaFreeHost(d->h_count);
     if (d->ev_count) cudaEventDestroy(d->ev_count);
     if (d->ev_sent) cudaEventDestroy(d->ev_sent);
+    if (d->ev_tick) cudaEventDestroy(d->ev_tick);
     if (d->ev_copied) cudaEventDestroy(d->ev_copied);
     if (d->rank == 0 && d->group) delete[] d->group;
     delete d;
@@ -177,6 +179,7 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     if (e == cudaSuccess) e = cudaHostAlloc(&d->h_count, 4, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_count, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_sent, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_tick, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_copied, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         dist_free(f); field_free(f); delete f;
@@ -205,8 +208,8 @@ static uint32_t read_upper_bound(flk_field *f) {
 
 // phase 1 of a tick on one strip: clear the outgoing messages, step (or re-stage) every owned bird.
 // Successors that go into a message can only come from the two owned columns next to each boundary (a bird moves
-// less than one column per tick) and from the slack column, so those columns are stepped FIRST; the exchange then
-// runs on the comm stream while the interior columns are stepped (north star: halo exchange overlapped with
+// less than one column per tick) and from the slack column, so those columns are stepped on the comm stream, which
+// then runs the exchange, while the interior columns are stepped on the main stream (north star: halo exchange overlapped with
 // interior-cell compute on separate streams).
 static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const float2 *d_inj, uint32_t n_inj, int identity) {
     flk_dist_state *d = f->dist;
@@ -229,15 +232,18 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
     const bool split = nown >= 5 && d->overlap;
     if (split) {
         // border: columns {ghost, 1, 2} and {nown-1, nown, ghost, slack} (ghost threads only invalidate their WRITE
-        // slot); the grid covers capx birds per range and the kernel flags ERR_EXCHANGE if a range holds more
-        // (capx is 8x the mean population of two columns)
+        // slot), on the high-priority comm stream so that they run BESIDE the interior launch instead of ahead of it
+        // (two launches of ~500 CTAs would leave most of the GPU idle).  The grid covers capx birds per range and the
+        // kernel flags ERR_EXCHANGE if a range holds more (capx is 8x the mean population of two columns).
+        CUDA_TRY(cudaEventRecord(d->ev_tick, f->stream));            // previous rebin + header clears are done
+        CUDA_TRY(cudaStreamWaitEvent(d->comm_stream, d->ev_tick, 0));
         const uint32_t ranges[2][2] = {{0, 3 * dh}, {(nown - 1) * dh, (nown + 3) * dh}};
         for (int r = 0; r < 2; ++r) {
             a.cell_lo = ranges[r][0]; a.cell_hi = ranges[r][1];
-            launch_step(f->g, f->p, f->s, a, f->s.capx, f->stream);
+            launch_step(f->g, f->p, f->s, a, f->s.capx, d->comm_stream);
             f->launches += 1;
         }
-        CUDA_TRY(cudaEventRecord(d->ev_sent, f->stream));
+        CUDA_TRY(cudaEventRecord(d->ev_sent, d->comm_stream));
         a.cell_lo = 3 * dh; a.cell_hi = (nown - 1) * dh;
         launch_step(f->g, f->p, f->s, a, read_upper_bound(f), f->stream);
         f->launches += 1;
