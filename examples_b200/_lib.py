@@ -22,6 +22,7 @@ _P = C.POINTER
 # name -> argtypes (every function returns int unless listed in _RESTYPE)
 SIGNATURES = {
     "flk_field_create": [_f32, _f32, _f32, C.c_int, _u64, C.c_int, _P(_vp)],
+    "flk_field_create_ex": [_f32, _f32, _f32, C.c_int, _u64, C.c_int, _u32, _P(_vp)],
     "flk_field_destroy": [_vp],
     "flk_field_clear": [_vp],
     "flk_set_params": [_vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, C.c_int],
@@ -29,6 +30,8 @@ SIGNATURES = {
     "flk_field_dims": [_vp, _P(_i32), _P(_i32), _P(_i32), _P(_i32)],
     "flk_set_object_location": [_vp, _u32, _f32, _f32, _f32, _f32],
     "flk_set_objects": [_vp, _u64, _vp, _vp, _vp],
+    "flk_set_objects_ex": [_vp, _u64, _vp, _vp, _vp, _vp],
+    "flk_snapshot_ex": [_vp, _vp, _vp, _vp, _vp, _P(_u64)],
     "flk_lazy_update": [_vp],
     "flk_step": [_vp, _u64, _u64, _vp, _u64],
     "flk_run": [_vp, _u64, _u64, _u64],

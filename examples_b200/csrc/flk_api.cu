@@ -51,6 +51,10 @@ int field_alloc(flk_field *f) {
     CUDA_TRY(cudaMalloc(&s.n_read_dev, 4));
     CUDA_TRY(cudaMalloc(&s.err_flag, 4));
     CUDA_TRY(cudaMemsetAsync(s.err_flag, 0, 4, f->stream));
+    if (s.pw) {
+        CUDA_TRY(cudaMalloc(&s.pay, cap * s.pw * 4));
+        CUDA_TRY(cudaMalloc(&s.tpay, capw * s.pw * 4));
+    }
     CUDA_TRY(cudaMemsetAsync(s.cell_start, 0, mp * 4, f->stream));
     CUDA_TRY(cudaMemsetAsync(s.cnt, 0, mp * 4, f->stream));
     CUDA_TRY(cudaMemsetAsync(s.step_dev, 0, 8, f->stream));
@@ -63,6 +67,9 @@ void field_free(flk_field *f) {
     cudaFree(s.rec); cudaFree(s.ids); cudaFree(s.cell_start); cudaFree(s.trec); cudaFree(s.tid);
     cudaFree(s.tkey); cudaFree(s.tslot); cudaFree(s.cnt); cudaFree(f->scratch); cudaFree(s.blocksum);
     cudaFree(s.step_dev); cudaFree(s.n_read_dev); cudaFree(s.err_flag);
+    if (s.pay) cudaFree(s.pay);
+    if (s.tpay) cudaFree(s.tpay);
+    if (f->d_paystage) cudaFree(f->d_paystage);
     if (f->d_injected) cudaFree(f->d_injected);
     if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
     for (auto &e : f->prof_events) cudaEventDestroy(e);
@@ -107,8 +114,20 @@ int flush_pending(flk_field *f) {
     return write_append(f, id.size(), id.data(), loc.data(), ld.data());
 }
 
-int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld) {
+int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld,
+                 const uint32_t *payload) {
     if (n == 0) return FLK_OK;
+    const uint32_t *d_pay = nullptr;
+    if (payload && f->s.pw) {
+        const uint64_t words = n * f->s.pw;
+        if (words > f->paystage_cap) {
+            if (f->d_paystage) { CUDA_TRY(cudaStreamSynchronize(f->stream)); cudaFree(f->d_paystage); f->d_paystage = nullptr; }
+            CUDA_TRY(cudaMalloc(&f->d_paystage, words * 4));
+            f->paystage_cap = words;
+        }
+        CUDA_TRY(cudaMemcpyAsync(f->d_paystage, payload, words * 4, cudaMemcpyHostToDevice, f->stream));
+        d_pay = f->d_paystage;
+    }
     if (f->w_count + n > f->cap)
         return fail(FLK_E_CAPACITY, "WRITE buffer would hold %llu objects, capacity is %llu",
                     (unsigned long long)(f->w_count + n), (unsigned long long)f->cap);
@@ -119,7 +138,7 @@ int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc,
     CUDA_TRY(cudaMemcpyAsync(d_id, id, n * 4, cudaMemcpyHostToDevice, f->stream));
     CUDA_TRY(cudaMemcpyAsync(d_loc, loc, n * 8, cudaMemcpyHostToDevice, f->stream));
     CUDA_TRY(cudaMemcpyAsync(d_ld, ld, n * 8, cudaMemcpyHostToDevice, f->stream));
-    launch_ingest(f->g, f->s, (uint32_t)n, d_id, d_loc, d_ld, (uint32_t)f->w_count, 1, f->stream);
+    launch_ingest(f->g, f->s, (uint32_t)n, d_id, d_loc, d_ld, d_pay, (uint32_t)f->w_count, 1, f->stream);
     f->launches += 1;
     CUDA_TRY(cudaGetLastError());
     f->w_count += n;
@@ -188,7 +207,13 @@ const char *flk_version(void) { return "flk 0.1 (sm_100a)"; }
 
 int flk_field_create(float width, float height, float discretization, int toroidal, uint64_t capacity, int device,
                      flk_field **out) {
+    return flk_field_create_ex(width, height, discretization, toroidal, capacity, device, 0, out);
+}
+
+int flk_field_create_ex(float width, float height, float discretization, int toroidal, uint64_t capacity, int device,
+                        uint32_t payload_bytes, flk_field **out) {
     if (!out) return fail(FLK_E_INVALID, "out is null");
+    if (payload_bytes % 4 != 0 || payload_bytes > 256) return fail(FLK_E_INVALID, "payload_bytes must be a multiple of 4, <= 256");
     *out = nullptr;
     if (capacity == 0 || capacity > 0x7fffffffull) return fail(FLK_E_INVALID, "capacity must be in [1, 2^31)");
     int ndev = 0;
@@ -205,6 +230,7 @@ int flk_field_create(float width, float height, float discretization, int toroid
     if (rc) { delete f; return rc; }
     f->cap = capacity;
     f->ncell = (uint32_t)f->g.ncols * (uint32_t)f->g.dh;
+    f->s.pw = payload_bytes / 4;
     CUDA_TRY(cudaSetDevice(device));
     CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&f->ev0));
@@ -283,6 +309,23 @@ int flk_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *l
     if (rc) return rc;
     if (f->g.mode == 1) return dist_set_objects(f, n, id, loc, last_d);
     return write_append(f, n, id, loc, last_d);
+}
+
+int flk_set_objects_ex(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *last_d,
+                       const void *payload) {
+    CHECK_HANDLE(f);
+    if (n && (!id || !loc || !last_d)) return fail(FLK_E_INVALID, "null array");
+    if (f->g.mode == 1) return fail(FLK_E_UNSUPPORTED, "payloads are not carried by strip handles");
+    int rc = flush_pending(f);
+    if (rc) return rc;
+    return write_append(f, n, id, loc, last_d, static_cast<const uint32_t *>(payload));
+}
+
+int flk_snapshot_ex(flk_field *f, uint32_t *id, float *loc, float *last_d, void *payload, uint64_t *n) {
+    CHECK_HANDLE(f);
+    if (payload && f->s.pw && f->n_read)
+        CUDA_TRY(cudaMemcpyAsync(payload, f->s.pay, f->n_read * f->s.pw * 4, cudaMemcpyDeviceToHost, f->stream));
+    return flk_snapshot(f, id, loc, last_d, n);
 }
 
 int flk_lazy_update(flk_field *f) {

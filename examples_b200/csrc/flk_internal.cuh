@@ -22,6 +22,8 @@ struct flk_field {
     uint64_t w_count = 0;    // WRITE slots in use
     std::vector<uint32_t> pend_id;   // buffered single set_object_location calls
     std::vector<float> pend_loc, pend_ld;
+    uint32_t *d_paystage = nullptr;   // upload staging of payload words
+    uint64_t paystage_cap = 0;
     float2 *d_injected = nullptr;
     uint64_t injected_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -58,7 +60,8 @@ int update_window(flk_field *f);
 int field_alloc(flk_field *f);
 void field_free(flk_field *f);
 int flush_pending(flk_field *f);
-int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld);
+int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld,
+                 const uint32_t *payload = nullptr);
 int upload_injected(flk_field *f, const float *r, uint64_t n);
 int enqueue_step(flk_field *f, uint64_t step, int use_step_dev, uint64_t seed, const float2 *d_inj, uint32_t n_inj);
 int enqueue_lazy_update(flk_field *f, int bump_step);

@@ -188,7 +188,9 @@ __device__ __forceinline__ void xbuf_append(const Store &s, uint8_t *buf, const 
 }
 
 __device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, const Rec &out, uint32_t id, uint32_t w,
-                                               bool d_ok, const Recip &Rd) {
+                                               bool d_ok, const Recip &Rd, uint32_t src) {
+    // Field2D<O>: whatever else the object carries moves with it (set_object_location stores the whole object)
+    for (uint32_t k = 0; k < s.pw; ++k) s.tpay[(size_t)w * s.pw + k] = s.pay[(size_t)src * s.pw + k];
     const int ncx = d_ok ? cell_coord_fast(out.x, Rd, g.mx + 1) : cell_coord(out.x, g.d, g.mx + 1);
     const int ncy = d_ok ? cell_coord_fast(out.y, Rd, g.dh) : cell_coord(out.y, g.d, g.dh);
     const int nlc = local_col(g, ncx);
@@ -236,7 +238,8 @@ constexpr int TILE_CAP = 256;   // records staged per window column (4 KB); 3 co
 // everything of Bird::step after the neighbour loop (bird.rs:73-145) + set_object_location
 template <int MATH>
 __device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, const Store &s, const StepArgs &a, const Rec &me,
-                                            uint32_t my_id, uint32_t w, const Acc &acc, bool d_ok, const Recip &Rd) {
+                                            uint32_t my_id, uint32_t w, const Acc &acc, bool d_ok, const Recip &Rd,
+                                            uint32_t src) {
     const float W = g.W, H = g.H;
     float xa = acc.xa, ya = acc.ya, xc = acc.xc, yc = acc.yc, xs = acc.xs, ys = acc.ys;
     const uint32_t nvec = acc.nvec;
@@ -305,7 +308,7 @@ __device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, cons
     out.x = toroidal_transform(__fadd_rn(me.x, dx), W);                              // :137
     out.y = toroidal_transform(__fadd_rn(me.y, dy), H);                              // :138
 
-    emit_successor(g, s, out, my_id, w, d_ok, Rd);   // :142-144
+    emit_successor(g, s, out, my_id, w, d_ok, Rd, src);   // :142-144
 }
 
 // interior accumulation out of the CTA's shared-memory tile (same order, same arithmetic as accumulate_interior)
@@ -423,7 +426,7 @@ __global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS) k_step(const Geom g, 
         return;
     }
     if (a.identity) {
-        emit_successor(g, s, me, my_id, w, d_ok, Rd);
+        emit_successor(g, s, me, my_id, w, d_ok, Rd, i);
         return;
     }
 
@@ -449,7 +452,7 @@ __global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS) k_step(const Geom g, 
         if (interior && RELAX) accumulate_interior<MATH>(g, s, me, i, lc, cy, acc);
         else accumulate_window<RELAX, MATH>(g, p, s, me, i, lc, cy, acc);
     }
-    finish_bird<MATH>(g, p, s, a, me, my_id, w, acc, d_ok, Rd);
+    finish_bird<MATH>(g, p, s, a, me, my_id, w, acc, d_ok, Rd, i);
 }
 
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
@@ -474,7 +477,7 @@ void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_ingest(const Geom g, const Store s, uint32_t n, const uint32_t *__restrict__ id,
                                                 const float2 *__restrict__ loc, const float2 *__restrict__ ld,
-                                                uint32_t base, int owned_only) {
+                                                const uint32_t *__restrict__ payload, uint32_t base, int owned_only) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const float2 l = loc[j], d = ld[j];
@@ -493,12 +496,14 @@ __global__ void __launch_bounds__(256) k_ingest(const Geom g, const Store s, uin
     s.tid[base + j] = id[j];
     s.tkey[base + j] = key;
     s.tslot[base + j] = slot;
+    for (uint32_t k = 0; k < s.pw; ++k)
+        s.tpay[(size_t)(base + j) * s.pw + k] = payload ? payload[(size_t)j * s.pw + k] : 0u;
 }
 
 void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id, const float2 *loc,
-                   const float2 *ld, uint32_t base, int owned_only, cudaStream_t st) {
+                   const float2 *ld, const uint32_t *payload, uint32_t base, int owned_only, cudaStream_t st) {
     if (n == 0) return;
-    k_ingest<<<(n + 255) / 256, 256, 0, st>>>(g, s, n, id, loc, ld, base, owned_only);
+    k_ingest<<<(n + 255) / 256, 256, 0, st>>>(g, s, n, id, loc, ld, payload, base, owned_only);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -681,6 +686,7 @@ __global__ void __launch_bounds__(256) k_rank(const Store s, uint32_t ncell, int
     const uint32_t dst = lo + r;
     reinterpret_cast<float4 *>(s.rec)[dst] = reinterpret_cast<const float4 *>(s.trec)[mine.y];
     s.ids[dst] = my_id;
+    for (uint32_t k = 0; k < s.pw; ++k) s.pay[(size_t)dst * s.pw + k] = s.tpay[(size_t)mine.y * s.pw + k];
 }
 
 void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st) {

@@ -22,6 +22,10 @@ struct Store {
     uint64_t *step_dev;    // tick counter used by graph replays
     uint32_t *n_read_dev;  // number of READ objects (device copy)
     uint32_t *err_flag;    // device-side error bits (ERR_*)
+    // generic Field2D<O> payload: pw 32-bit words per object carried along with its record (0 = none)
+    uint32_t *pay;         // READ payload [cap*pw]
+    uint32_t *tpay;        // WRITE payload
+    uint32_t pw;
     uint32_t cap;          // READ / stepped-WRITE capacity
     // strip decomposition only: fixed-capacity exchange buffers, XHdr | Rec[capx] | id[capx]
     uint32_t capx;
@@ -53,7 +57,7 @@ struct StepArgs {
 };
 
 void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id, const float2 *loc,
-                   const float2 *ld, uint32_t base, int owned_only, cudaStream_t st);
+                   const float2 *ld, const uint32_t *payload, uint32_t base, int owned_only, cudaStream_t st);
 void launch_unpack(const Geom &g, const Store &s, cudaStream_t st);
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st);

@@ -55,10 +55,13 @@ def _vp(a):
 class Field2D:
     """GPU-resident Field2D<Bird>: READ buffer sorted by (cell, id), WRITE buffer in arrival order."""
 
-    def __init__(self, width, height, discretization=DISCRETIZATION, toroidal=TOROIDAL, capacity=1 << 20, device=0):
+    def __init__(self, width, height, discretization=DISCRETIZATION, toroidal=TOROIDAL, capacity=1 << 20, device=0,
+                 payload_words=0):
         self._L = _lib.load()
         self._h = C.c_void_p()
-        check(self._L.flk_field_create(width, height, discretization, int(toroidal), capacity, device, C.byref(self._h)))
+        self.payload_words = payload_words   # Field2D<O>: extra 32-bit words every object carries (0 for Bird)
+        check(self._L.flk_field_create_ex(width, height, discretization, int(toroidal), capacity, device,
+                                          4 * payload_words, C.byref(self._h)))
         self.width, self.height, self.discretization, self.toroidal = width, height, discretization, toroidal
         self.capacity = capacity
         dw, dh, mx, my = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
@@ -70,6 +73,7 @@ class Field2D:
         self = cls.__new__(cls)
         self._L = _lib.load()
         self._h = handle
+        self.payload_words = 0
         self.width, self.height, self.discretization, self.toroidal = width, height, discretization, True
         self.capacity = capacity
         dw, dh, mx, my = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
@@ -106,13 +110,18 @@ class Field2D:
     def set_object_location(self, bird: Bird, loc: Real2D):
         check(self._L.flk_set_object_location(self._h, bird.id, loc.x, loc.y, bird.last_d.x, bird.last_d.y))
 
-    def set_objects(self, ids: np.ndarray, loc: np.ndarray, last_d: np.ndarray):
+    def set_objects(self, ids: np.ndarray, loc: np.ndarray, last_d: np.ndarray, payload: np.ndarray | None = None):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         loc = np.ascontiguousarray(loc, dtype=np.float32)
         last_d = np.ascontiguousarray(last_d, dtype=np.float32)
         n = len(ids)
         assert loc.size == 2 * n and last_d.size == 2 * n
-        check(self._L.flk_set_objects(self._h, n, _vp(ids), _vp(loc), _vp(last_d)))
+        if payload is not None:
+            payload = np.ascontiguousarray(payload, dtype=np.uint32)
+            assert payload.size == n * getattr(self, "payload_words", 0)
+            check(self._L.flk_set_objects_ex(self._h, n, _vp(ids), _vp(loc), _vp(last_d), _vp(payload)))
+        else:
+            check(self._L.flk_set_objects(self._h, n, _vp(ids), _vp(loc), _vp(last_d)))
 
     def set_objects_raw(self, n, id_ptr, loc_ptr, ld_ptr):
         """Pointer form (pinned torch tensors in bench.py)."""
@@ -205,6 +214,18 @@ class Field2D:
         check(self._L.flk_snapshot(self._h, _vp(ids), _vp(loc), _vp(ld), C.byref(cnt)))
         k = cnt.value
         return ids[:k], loc[:k], ld[:k]
+
+    def snapshot_with_payload(self):
+        """(ids, loc, last_d, payload[n, payload_words]) of the READ buffer in (cell, id) order"""
+        n = self.capacity
+        ids = np.zeros(n, dtype=np.uint32)
+        loc = np.zeros((n, 2), dtype=np.float32)
+        ld = np.zeros((n, 2), dtype=np.float32)
+        pay = np.zeros((n, max(self.payload_words, 1)), dtype=np.uint32)
+        cnt = C.c_uint64()
+        check(self._L.flk_snapshot_ex(self._h, _vp(ids), _vp(loc), _vp(ld), _vp(pay), C.byref(cnt)))
+        k = cnt.value
+        return ids[:k], loc[:k], ld[:k], pay[:k, : self.payload_words]
 
     def snapshot_raw(self, id_ptr, loc_ptr, ld_ptr) -> int:
         cnt = C.c_uint64()

@@ -47,6 +47,11 @@ typedef struct flk_field flk_field;
  * capacity = max number of objects the field will ever hold; device = CUDA ordinal. */
 int flk_field_create(float width, float height, float discretization, int toroidal,
                      uint64_t capacity, int device, flk_field **out);
+/* Field2D<O> for an object type that carries more than Bird's {id, loc, last_d} (template/src/model/crab.rs:11-19,
+ * virusnetwork/src/model/node.rs): payload_bytes (multiple of 4, <= 256) opaque bytes per object travel with it through
+ * set_object_location, Bird::step (copied unchanged to the successor) and lazy_update.  Single-GPU handles only. */
+int flk_field_create_ex(float width, float height, float discretization, int toroidal, uint64_t capacity, int device,
+                        uint32_t payload_bytes, flk_field **out);
 int flk_field_destroy(flk_field *f);
 
 /* State::reset re-creates the field (flockers/src/model/state.rs:32-35): drop every object, keep memory. */
@@ -73,6 +78,10 @@ int flk_set_object_location(flk_field *f, uint32_t id, float x, float y, float l
 
 /* bulk form of the above (n birds; HOST arrays; loc/last_d interleaved x,y) */
 int flk_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *last_d);
+
+/* flk_set_objects with n * payload_bytes bytes of payload (NULL = zero-filled) */
+int flk_set_objects_ex(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *last_d,
+                       const void *payload);
 
 /* Field::lazy_update()   flockers/src/model/state.rs:54-56
  * WRITE becomes READ (re-binned by cell, ascending id inside a cell), the new WRITE buffer is empty.
@@ -119,6 +128,9 @@ int flk_snapshot(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t
  * Looks one object up by id in the READ buffer (the reference hashes Bird by id, bird.rs:148-163).  Synchronous.
  * *found = 0 when no object has that id (the reference returns None); out = {x, y, last_d.x, last_d.y}. */
 int flk_get_object(flk_field *f, uint32_t id, float out[4], int32_t *found);
+
+/* flk_snapshot plus the payload bytes, same order */
+int flk_snapshot_ex(flk_field *f, uint32_t *id, float *loc, float *last_d, void *payload, uint64_t *n);
 
 /* the binning itself: cell_start[dw*dh+1] (flat cell = cx*dh+cy) and ids in sorted order */
 int flk_get_binning(flk_field *f, uint32_t *cell_start, uint32_t *sorted_ids);

@@ -13,6 +13,8 @@ pub const FLK_E_CAPACITY: c_int = -3;
 extern "C" {
     pub fn flk_field_create(width: c_float, height: c_float, discretization: c_float, toroidal: c_int, capacity: u64,
                             device: c_int, out: *mut *mut flk_field) -> c_int;
+    pub fn flk_field_create_ex(width: c_float, height: c_float, discretization: c_float, toroidal: c_int, capacity: u64,
+                               device: c_int, payload_bytes: u32, out: *mut *mut flk_field) -> c_int;
     pub fn flk_field_destroy(f: *mut flk_field) -> c_int;
     pub fn flk_field_clear(f: *mut flk_field) -> c_int;
     pub fn flk_set_params(f: *mut flk_field, cohesion: c_float, avoidance: c_float, randomness: c_float,
@@ -21,6 +23,10 @@ extern "C" {
     pub fn flk_field_dims(f: *const flk_field, dw: *mut i32, dh: *mut i32, mx: *mut i32, my: *mut i32) -> c_int;
     pub fn flk_set_object_location(f: *mut flk_field, id: u32, x: c_float, y: c_float, ldx: c_float, ldy: c_float) -> c_int;
     pub fn flk_set_objects(f: *mut flk_field, n: u64, id: *const u32, loc: *const c_float, last_d: *const c_float) -> c_int;
+    pub fn flk_set_objects_ex(f: *mut flk_field, n: u64, id: *const u32, loc: *const c_float, last_d: *const c_float,
+                              payload: *const c_void) -> c_int;
+    pub fn flk_snapshot_ex(f: *mut flk_field, id: *mut u32, loc: *mut c_float, last_d: *mut c_float, payload: *mut c_void,
+                           n: *mut u64) -> c_int;
     pub fn flk_lazy_update(f: *mut flk_field) -> c_int;
     pub fn flk_step(f: *mut flk_field, step: u64, seed: u64, injected_r: *const c_float, n_injected: u64) -> c_int;
     pub fn flk_run(f: *mut flk_field, first_step: u64, n_steps: u64, seed: u64) -> c_int;

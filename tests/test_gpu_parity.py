@@ -134,6 +134,46 @@ def test_single_query_api_and_capacity_code():
     assert rc == _lib.E_CAPACITY and n.value == len(want) and np.array_equal(ids, want[:4])
 
 
+def test_payload_travels_with_its_object():
+    """Field2D<O> with an object that carries more than Bird (template's Crab, virusnetwork's NetNode): the extra
+    words follow their id through set_object_location, Bird::step and lazy_update; the Bird fields are unaffected."""
+    from examples_b200 import Field2D
+    n, W = 5000, 300.0
+    birds = uniform_birds(n, W, W)
+    ids, loc, ld = to_arrays(birds)
+    pay = np.stack([ids * 7 + 1, ids ^ 0xABCD, np.arange(n, dtype=np.uint32)[::-1]], axis=1).astype(np.uint32)
+    f = Field2D(W, W, D, True, capacity=n, payload_words=3)
+    f.set_objects(ids, loc, ld, payload=pay)
+    f.lazy_update()
+    plain = load_gpu(birds, W, W)
+    for t0 in (0, 10):
+        f.run(t0, 10)
+        plain.run(t0, 10)
+        gi, gl, gd, gp = f.snapshot_with_payload()
+        assert np.array_equal(gp, pay[gi])                                   # payload still attached to its id
+        o = np.argsort(gi, kind="stable")
+        assert bits_equal(from_arrays(gi[o], gl[o], gd[o]), gpu_state(plain))   # and the flock is the same flock
+
+
+def test_non_toroidal_field_queries_match_oracle():
+    """Field2D::new(w, h, d, false) as in virusnetwork/src/main.rs:17: the query window is clamped, not wrapped"""
+    from examples_b200 import Field2D
+    W = 100.0
+    birds = uniform_birds(800, W, W)
+    f = Field2D(W, W, D, False, capacity=800)
+    f.set_objects(*to_arrays(birds))
+    f.lazy_update()
+    fo = O.Field(W, W, toroidal=False)
+    fo.set_objects(birds)
+    fo.lazy_update()
+    probes = np.array([[0.5, 0.5], [99.5, 99.5], [50.0, 50.0], [0.1, 50.0], [99.9, 3.0], [100.0, 100.0]], dtype=np.float32)
+    for relax in (True, False):
+        off, ids = f.query_batch(probes, 10.0, relax=relax)
+        for q, (x, y) in enumerate(probes):
+            want = fo.neighbors(x, y, 10.0, relax=relax)["id"]
+            assert np.array_equal(ids[int(off[q]):int(off[q + 1])], want), (relax, q)
+
+
 def test_get_and_get_location_by_id():
     """Field2D::get / get_location (visualization accessors): lookup by id in the READ buffer"""
     birds = uniform_birds(1000, 100.0, 100.0)
