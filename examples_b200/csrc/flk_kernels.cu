@@ -654,16 +654,54 @@ __global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n, uint
     s.stage[p] = make_uint4(s.tid[i], i, key, 0u);   // one 16-byte store instead of three scattered 4-byte ones
 }
 
+// four consecutive stepped/uploaded slots per thread: three 16-byte loads, then four independent gather -> store
+// chains in flight (the one-slot-per-thread form reached 42 % of DRAM bandwidth: too few bytes in flight per thread)
+__global__ void __launch_bounds__(256) k_scatter4(const Store s, uint32_t n_limit, int use_dev_count) {
+    const uint32_t n = use_dev_count ? min(*s.n_read_dev, n_limit) : n_limit;
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (i0 >= n) return;
+    uint32_t key[4], slot[4], id[4];
+    if (i0 + 4 <= n) {
+        const uint4 k4 = *reinterpret_cast<const uint4 *>(s.tkey + i0);
+        const uint4 s4 = *reinterpret_cast<const uint4 *>(s.tslot + i0);
+        const uint4 d4 = *reinterpret_cast<const uint4 *>(s.tid + i0);
+        key[0] = k4.x; key[1] = k4.y; key[2] = k4.z; key[3] = k4.w;
+        slot[0] = s4.x; slot[1] = s4.y; slot[2] = s4.z; slot[3] = s4.w;
+        id[0] = d4.x; id[1] = d4.y; id[2] = d4.z; id[3] = d4.w;
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const bool ok = i0 + t < n;
+            key[t] = ok ? s.tkey[i0 + t] : KEY_INVALID;
+            slot[t] = ok ? s.tslot[i0 + t] : 0u;
+            id[t] = ok ? s.tid[i0 + t] : 0u;
+        }
+    }
+    uint32_t base[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) base[t] = key[t] != KEY_INVALID ? __ldg(s.cell_start + key[t]) : 0u;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (key[t] == KEY_INVALID) continue;
+        const uint32_t p = base[t] + slot[t];
+        if (p >= s.cap) {
+            atomicOr(s.err_flag, ERR_CAPACITY);
+            continue;
+        }
+        s.stage[p] = make_uint4(id[t], i0 + t, key[t], 0u);
+    }
+}
+
 void launch_scatter(const Store &s, uint32_t n, int dist, cudaStream_t st) {
     if (dist) {
         // stepped slots [0, n) (n = host upper bound of the READ population), then the two receive regions
         const uint32_t nn = n < s.cap ? n : s.cap;
-        if (nn) k_scatter<true><<<(nn + 255) / 256, 256, 0, st>>>(s, nn, 0);
+        if (nn) k_scatter4<<<((nn + 3) / 4 + 255) / 256, 256, 0, st>>>(s, nn, 1);
         k_scatter<true><<<(2 * s.capx + 255) / 256, 256, 0, st>>>(s, 2 * s.capx, s.cap);
         return;
     }
     if (n == 0) return;
-    k_scatter<false><<<(n + 255) / 256, 256, 0, st>>>(s, n, 0);
+    k_scatter4<<<((n + 3) / 4 + 255) / 256, 256, 0, st>>>(s, n, 0);
 }
 
 __global__ void __launch_bounds__(256) k_rank(const Store s, uint32_t ncell, int bump_step) {
