@@ -100,6 +100,8 @@ int update_window(flk_field *f) {
         return fail(FLK_E_UNSUPPORTED, "query window (%d cells) wider than the grid (%d x %d): duplicate visits are not implemented",
                     2 * k + 1, f->g.mx, f->g.my);
     if (f->g.mode == 1 && k > 1) return fail(FLK_E_UNSUPPORTED, "strip decomposition implements a one-column halo (k<=1), got k=%d", k);
+    if (f->g.mode == 1 && !(std::fabs(f->p.jump) < f->g.d))
+        return fail(FLK_E_UNSUPPORTED, "strip decomposition needs |jump| < discretisation (a bird may cross one column per tick)");
     f->p.k = k;
     return FLK_OK;
 }
