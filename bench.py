@@ -291,28 +291,81 @@ def run_ours(args, world: int, rank: int, local_rank: int):
 
     # ---- e2e: per step, host -> device copy of every agent, one tick, device -> host read of the new state ----
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
-    o_id = torch.empty_like(h_id).pin_memory()      # empty_like of a pinned tensor is pageable: pin explicitly
-    o_loc = torch.empty_like(h_loc).pin_memory()
-    o_ld = torch.empty_like(h_ld).pin_memory()
-    assert o_id.is_pinned() and o_loc.is_pinned() and o_ld.is_pinned() and h_id.is_pinned() and h_loc.is_pinned()
-    ids_np = None
-    for it in range(e2e_steps + 1):
-        if it == 1:
+    e2e_extra = {}
+    if world == 1:
+        # The host keeps the agents as a list indexed by id (flockers/src/model/state.rs:40-51), so the dense C-ABI
+        # calls move Bird minus its id: 16 B per bird each way.  Every step of every repetition uploads all agents
+        # from pinned host memory, publishes them (lazy_update), runs Bird::step + lazy_update and downloads all
+        # agents; the download is the next step's upload (a dependent chain per repetition).  `reps` independent
+        # repetitions (simulate!'s third argument, flockers/src/main.rs:47) are pipelined over one handle each, so
+        # one repetition's download overlaps the next one's upload on the two PCIe directions.
+        rec0 = np.concatenate([loc, np.zeros_like(loc)], axis=1)
+
+        def e2e_run(fields, steps):
+            R = len(fields)
+            h_in = [torch.from_numpy(rec0.copy()).pin_memory() for _ in range(R)]
+            h_out = [torch.empty((n_local, 4), dtype=torch.float32).pin_memory() for _ in range(R)]
+            assert all(t.is_pinned() for t in h_in + h_out)
+            t0 = 0.0
+            for it in range(steps + 1):          # iteration 0 is untimed (first-touch, graph/alloc warm-up)
+                if it == 1:
+                    for fr in fields:
+                        fr.synchronize()
+                    barrier()
+                    t0 = time.perf_counter()
+                for r, fr in enumerate(fields):
+                    fr.synchronize()             # this repetition's previous download has landed
+                    fr.set_objects_dense_raw(n_local, h_in[r].data_ptr())
+                    fr.commit()
+                    fr.run(1000 + it, 1, STEP_SEED + r)
+                    fr.snapshot_dense_async_raw(n_local, h_out[r].data_ptr())
+                    h_in[r], h_out[r] = h_out[r], h_in[r]
+            for fr in fields:
+                fr.synchronize()
             barrier()
-            t0 = time.perf_counter()
-        f.set_objects_raw(n_local, h_id.data_ptr(), h_loc.data_ptr(), h_ld.data_ptr())
-        f.commit()
-        f.run(1000 + it, 1, STEP_SEED)
-        got = f.snapshot_owned_raw(o_id.data_ptr(), o_loc.data_ptr(), o_ld.data_ptr())
-        # the host keeps the agents: next step's input is this step's output (ids follow the records)
-        h_id, o_id = o_id, h_id
-        h_loc, o_loc = o_loc, h_loc
-        h_ld, o_ld = o_ld, h_ld
-        n_local_now = got
-        n_local = n_local_now if world > 1 else n_local
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = n_total * e2e_steps / e2e_s
+            dt = time.perf_counter() - t0
+            for r in range(R):                   # every agent came back (no NaN rows), and it moved
+                assert not bool(torch.isnan(h_in[r][:: max(n_local // 4096, 1)]).any())
+            return R * n_local * steps / dt
+
+        serial_value = e2e_run([f], e2e_steps)
+        reps = max(1, args.e2e_reps)
+        extra = [Field2D(W, H, D, True, capacity=cap, device=local_rank) for _ in range(reps - 1)]
+        for fx in extra:
+            fx.set_math_mode(args.math)
+        e2e_value = e2e_run([f] + extra, e2e_steps)
+        for fx in extra:
+            fx.close()
+        e2e_bytes = 16 * n_local
+        e2e_extra = {"reps": reps, "serial_value": serial_value,
+                     "what": f"{reps} independent repetitions pipelined over {reps} handles; per step and repetition: "
+                             "flk_set_objects_dense(pinned host, 16 B/bird) + lazy_update + Bird::step + lazy_update + "
+                             "flk_snapshot_dense_async(pinned host, 16 B/bird); output feeds the next step's input; "
+                             "serial_value = one repetition alone (no overlap)"}
+    else:
+        o_id = torch.empty_like(h_id).pin_memory()      # empty_like of a pinned tensor is pageable: pin explicitly
+        o_loc = torch.empty_like(h_loc).pin_memory()
+        o_ld = torch.empty_like(h_ld).pin_memory()
+        assert o_id.is_pinned() and o_loc.is_pinned() and o_ld.is_pinned() and h_id.is_pinned() and h_loc.is_pinned()
+        for it in range(e2e_steps + 1):
+            if it == 1:
+                barrier()
+                t0 = time.perf_counter()
+            f.set_objects_raw(n_local, h_id.data_ptr(), h_loc.data_ptr(), h_ld.data_ptr())
+            f.commit()
+            f.run(1000 + it, 1, STEP_SEED)
+            got = f.snapshot_owned_raw(o_id.data_ptr(), o_loc.data_ptr(), o_ld.data_ptr())
+            # the host keeps the agents: next step's input is this step's output (ids follow the records)
+            h_id, o_id = o_id, h_id
+            h_loc, o_loc = o_loc, h_loc
+            h_ld, o_ld = o_ld, h_ld
+            n_local = got
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_value = n_total * e2e_steps / e2e_s
+        e2e_bytes = 20 * (n_total // world)
+        e2e_extra = {"what": "per rank: flk_set_objects(host) + commit + Bird::step + exchange + lazy_update + "
+                             "flk_dist_snapshot_owned(host) per step, 20 B/bird each way"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on the host cores, bounded sample ----
     cpu = None
@@ -339,9 +392,8 @@ def run_ours(args, world: int, rank: int, local_rank: int):
                          "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
                          "note": "path is FP32-issue bound, not HBM bound (DESIGN.md roofline)"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "bird-updates/s", "h2d_bytes_per_step": 20 * (n_total // world),
-                    "d2h_bytes_per_step": 20 * (n_total // world), "steps": e2e_steps,
-                    "what": "flk_set_objects(host) + lazy_update + Bird::step + lazy_update + flk_snapshot(host) per step"},
+            "e2e": {"value": e2e_value, "unit": "bird-updates/s", "h2d_bytes_per_step": e2e_bytes,
+                    "d2h_bytes_per_step": e2e_bytes, "steps": e2e_steps, **e2e_extra},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -360,7 +412,8 @@ def main():
     ap.add_argument("--workload", default="weak16m", choices=["weak16m", "strong16m", "1m", "clustered"])
     ap.add_argument("--birds-per-gpu", type=int, default=None)
     ap.add_argument("--math", type=int, default=0)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-reps", type=int, default=3)           # independent repetitions pipelined in the e2e leg
     ap.add_argument("--cpu-birds", type=int, default=1_000_000)   # birds of the CPU sample (per tick)
     ap.add_argument("--cpu-ticks", type=int, default=200)        # ~10 s of CPU work on 16 cores
     ap.add_argument("--no-cpu-baseline", action="store_true")

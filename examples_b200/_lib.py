@@ -40,6 +40,10 @@ SIGNATURES = {
     "flk_query_batch": [_vp, _u64, _vp, _f32, C.c_int, _vp, _vp, _u64],
     "flk_num_objects": [_vp, _P(_u64)],
     "flk_snapshot": [_vp, _vp, _vp, _vp, _P(_u64)],
+    "flk_snapshot_async": [_vp, _vp, _vp, _vp, _P(_u64)],
+    "flk_set_objects_dense": [_vp, _u64, _u32, _vp],
+    "flk_snapshot_dense": [_vp, _u32, _u64, _vp],
+    "flk_snapshot_dense_async": [_vp, _u32, _u64, _vp],
     "flk_get_binning": [_vp, _vp, _vp],
     "flk_get_object": [_vp, _u32, _P(_f32), _P(_i32)],
     "flk_synchronize": [_vp],

@@ -71,6 +71,7 @@ void field_free(flk_field *f) {
     if (s.tpay) cudaFree(s.tpay);
     if (f->d_paystage) cudaFree(f->d_paystage);
     if (f->d_injected) cudaFree(f->d_injected);
+    if (f->h_dense) cudaFreeHost(f->h_dense);
     if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
     for (auto &e : f->prof_events) cudaEventDestroy(e);
     for (auto &e : f->prof_rebin) cudaEventDestroy(e);
@@ -409,7 +410,7 @@ int flk_num_objects(const flk_field *f, uint64_t *n) {
     return FLK_OK;
 }
 
-int flk_snapshot(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n) {
+static int snapshot_impl(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n, bool sync) {
     CHECK_HANDLE(f);
     if (f->g.mode == 1) { int rc = dist_refresh_counts(f); if (rc) return rc; }
     const uint64_t nr = f->n_read;
@@ -426,8 +427,71 @@ int flk_snapshot(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t
         if (loc) CUDA_TRY(cudaMemcpyAsync(loc, d_loc, nr * 8, cudaMemcpyDeviceToHost, f->stream));
         if (last_d) CUDA_TRY(cudaMemcpyAsync(last_d, d_ld, nr * 8, cudaMemcpyDeviceToHost, f->stream));
     }
-    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    if (sync) CUDA_TRY(cudaStreamSynchronize(f->stream));
     return FLK_OK;
+}
+
+int flk_snapshot(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n) {
+    return snapshot_impl(f, id, loc, last_d, n, true);
+}
+
+int flk_snapshot_async(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n) {
+    return snapshot_impl(f, id, loc, last_d, n, false);
+}
+
+// ---- dense (id-indexed) host interface: 16 bytes per object each way ---------------------------------------------
+static uint32_t *dense_counter(flk_field *f) {
+    return reinterpret_cast<uint32_t *>(f->scratch + ((f->cap * 20 + 15) & ~(uint64_t)15) + 64);
+}
+
+int flk_set_objects_dense(flk_field *f, uint64_t n, uint32_t id0, const float *rec4) {
+    CHECK_HANDLE(f);
+    if (n && !rec4) return fail(FLK_E_INVALID, "null array");
+    if (f->g.mode == 1) return fail(FLK_E_UNSUPPORTED, "dense upload is for single-GPU handles (a strip owns arbitrary ids)");
+    if ((uint64_t)id0 + n > 0x100000000ull) return fail(FLK_E_INVALID, "id range exceeds u32");
+    int rc = flush_pending(f);
+    if (rc) return rc;
+    if (n == 0) return FLK_OK;
+    if (f->w_count + n > f->cap)
+        return fail(FLK_E_CAPACITY, "WRITE buffer would hold %llu objects, capacity is %llu",
+                    (unsigned long long)(f->w_count + n), (unsigned long long)f->cap);
+    float4 *d_rec = reinterpret_cast<float4 *>(f->scratch);   // staging (free outside lazy_update; stream order protects it)
+    CUDA_TRY(cudaMemcpyAsync(d_rec, rec4, n * 16, cudaMemcpyHostToDevice, f->stream));
+    launch_ingest_dense(f->g, f->s, (uint32_t)n, id0, d_rec, (uint32_t)f->w_count, f->stream);
+    f->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    f->w_count += n;
+    return FLK_OK;
+}
+
+static int snapshot_dense_impl(flk_field *f, uint32_t id0, uint64_t n, float *rec4, bool sync) {
+    CHECK_HANDLE(f);
+    if (n && !rec4) return fail(FLK_E_INVALID, "null array");
+    if (f->g.mode == 1) return fail(FLK_E_UNSUPPORTED, "dense snapshot is for single-GPU handles (a strip owns arbitrary ids)");
+    if (n > f->cap) return fail(FLK_E_CAPACITY, "id range %llu larger than the capacity %llu", (unsigned long long)n, (unsigned long long)f->cap);
+    if ((uint64_t)id0 + n > 0x100000000ull) return fail(FLK_E_INVALID, "id range exceeds u32");
+    if (n == 0) return FLK_OK;
+    if (!f->h_dense) CUDA_TRY(cudaHostAlloc(&f->h_dense, 4, cudaHostAllocDefault));
+    float4 *d_out = reinterpret_cast<float4 *>(f->scratch);
+    uint32_t *d_cnt = dense_counter(f);
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, f->stream));
+    if (f->n_read != n) CUDA_TRY(cudaMemsetAsync(d_out, 0xFF, n * 16, f->stream));   // ids not in the field read back as NaN
+    launch_gather_dense(f->s, (uint32_t)f->n_read, id0, (uint32_t)n, d_out, d_cnt, f->stream);
+    f->launches += f->n_read ? 1 : 0;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(rec4, d_out, n * 16, cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(cudaMemcpyAsync(f->h_dense, d_cnt, 4, cudaMemcpyDeviceToHost, f->stream));
+    f->dense_pending = true;
+    if (sync) return flk_synchronize(f);
+    return FLK_OK;
+}
+
+int flk_snapshot_dense(flk_field *f, uint32_t id0, uint64_t n, float *rec4) {
+    return snapshot_dense_impl(f, id0, n, rec4, true);
+}
+
+int flk_snapshot_dense_async(flk_field *f, uint32_t id0, uint64_t n, float *rec4) {
+    return snapshot_dense_impl(f, id0, n, rec4, false);
 }
 
 int flk_get_object(flk_field *f, uint32_t id, float out[4], int32_t *found) {
@@ -540,6 +604,11 @@ int flk_get_neighbors_within_distance(flk_field *f, float x, float y, float dist
 int flk_synchronize(flk_field *f) {
     CHECK_HANDLE(f);
     CUDA_TRY(cudaStreamSynchronize(f->stream));
+    if (f->dense_pending) {   // outcome of the last (possibly asynchronous) dense snapshot
+        f->dense_pending = false;
+        if (*f->h_dense)
+            return fail(FLK_E_INVALID, "dense snapshot: %u objects have ids outside the requested range", *f->h_dense);
+    }
     return FLK_OK;
 }
 

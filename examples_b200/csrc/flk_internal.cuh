@@ -25,6 +25,8 @@ struct flk_field {
     uint32_t *d_paystage = nullptr;   // upload staging of payload words
     uint64_t paystage_cap = 0;
     float2 *d_injected = nullptr;
+    uint32_t *h_dense = nullptr;      // pinned word: ids outside the range of the last dense snapshot
+    bool dense_pending = false;
     uint64_t injected_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // flk_run graph cache

@@ -313,12 +313,56 @@ __device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, cons
 
 // interior accumulation out of the CTA's shared-memory tile (same order, same arithmetic as accumulate_interior)
 #ifndef FLK_SMEM_UNROLL
-#define FLK_SMEM_UNROLL 2
+#define FLK_SMEM_UNROLL 1   // measured with the packed loop: unroll 1 0.877 ms, 2 0.909 ms, 4 0.912 ms (no odd-length remainder pass)
 #endif
 constexpr int kSmemUnroll = FLK_SMEM_UNROLL;
 // SELF: the run contains the bird itself at index `self` (bird.rs:53 skips it by id).  Its own record contributes
 // exactly nothing to the avoidance and cohesion sums (dx = dy = +0, 0/den = +0, and an accumulator that started at +0
 // is unchanged by adding +0), so only the consistency terms need a select — cheaper than splitting the run in two.
+// Packed form of the same loop for exact arithmetic: Blackwell's two-lane f32 instructions (add/mul/fma.rn.f32x2 ->
+// FADD2/FMUL2/FFMA2) carry the x and y halves of every step in one issue slot.  Each lane is the same IEEE
+// round-to-nearest operation as the scalar form, so results are bit-identical:
+//   (dx,dy) = fma(o.xy, -1, me.xy)   == me - o      (the product by -1 is exact, one rounding)
+//   nden    = (-sq*sq) + (-1)        == -(sq*sq+1)  (round-to-nearest is symmetric)
+#ifndef FLK_PACKED
+#define FLK_PACKED 1
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float a, float b) { f32x2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ void unpk(f32x2 d, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(d)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+template <bool SELF>
+__device__ __forceinline__ void accumulate_run_smem_packed(const float4 *tile, uint32_t j, uint32_t e, uint32_t self,
+                                                           f32x2 ME, f32x2 &A, f32x2 &Cc, f32x2 &Ss) {
+    const ulonglong2 *t2 = reinterpret_cast<const ulonglong2 *>(tile);
+    const f32x2 NEG1 = pk(-1.0f, -1.0f);
+#pragma unroll kSmemUnroll
+    for (; j < e; ++j) {
+        ulonglong2 o = t2[j];
+        if (SELF && j == self) o.y = 0ull;                     // (last_d) := (+0,+0), see accumulate_run_smem
+        const f32x2 Dv = fma2(o.x, NEG1, ME);                   // bird.rs:54-55 (no seam in reach)
+        const f32x2 Sv = mul2(Dv, Dv);
+        float s0, s1;
+        unpk(Sv, s0, s1);
+        const float sq = __fadd_rn(s0, s1);                    // :59
+        const float nden = __fadd_rn(-__fmul_rn(sq, sq), -1.0f);
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-nden));
+        const float er = __fmaf_rn(nden, r, 1.0f);             // div2_rn_interior, two lanes at a time
+        r = __fmaf_rn(r, er, r);
+        const f32x2 RR = pk(r, r), ND = pk(nden, nden);
+        const f32x2 Q0 = mul2(Dv, RR);
+        const f32x2 REM = fma2(ND, Q0, Dv);
+        const f32x2 Q = fma2(RR, REM, Q0);                      // :60-61
+        A = add2(A, Q);
+        Cc = add2(Cc, Dv);                                      // :64-65
+        Ss = add2(Ss, o.y);                                     // :68-69
+    }
+}
+
 template <int MATH, bool SELF>
 __device__ __forceinline__ void accumulate_run_smem(const float4 *tile, uint32_t j, uint32_t e, uint32_t self, float mx_,
                                                     float my_, float &xa, float &ya, float &xc, float &yc, float &xs,
@@ -438,9 +482,18 @@ __global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS) k_step(const Geom g, 
         const uint32_t a1 = __ldg(cs + g.dh), b1 = __ldg(cs + g.dh + 3);
         const uint32_t a2 = __ldg(cs + 2 * g.dh), b2 = __ldg(cs + 2 * g.dh + 3);
         float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
-        accumulate_run_smem<MATH, false>(tile[0], a0 - sA0, b0 - sA0, 0, me.x, me.y, xa, ya, xc, yc, xs, ys);
-        accumulate_run_smem<MATH, true>(tile[1], a1 - sA1, b1 - sA1, i - sA1, me.x, me.y, xa, ya, xc, yc, xs, ys);
-        accumulate_run_smem<MATH, false>(tile[2], a2 - sA2, b2 - sA2, 0, me.x, me.y, xa, ya, xc, yc, xs, ys);
+        if (MATH == 0 && FLK_PACKED) {
+            const f32x2 ME = pk(me.x, me.y);
+            f32x2 A = 0ull, Cc = 0ull, Ss = 0ull;
+            accumulate_run_smem_packed<false>(tile[0], a0 - sA0, b0 - sA0, 0, ME, A, Cc, Ss);
+            accumulate_run_smem_packed<true>(tile[1], a1 - sA1, b1 - sA1, i - sA1, ME, A, Cc, Ss);
+            accumulate_run_smem_packed<false>(tile[2], a2 - sA2, b2 - sA2, 0, ME, A, Cc, Ss);
+            unpk(A, xa, ya); unpk(Cc, xc, yc); unpk(Ss, xs, ys);
+        } else {
+            accumulate_run_smem<MATH, false>(tile[0], a0 - sA0, b0 - sA0, 0, me.x, me.y, xa, ya, xc, yc, xs, ys);
+            accumulate_run_smem<MATH, true>(tile[1], a1 - sA1, b1 - sA1, i - sA1, me.x, me.y, xa, ya, xc, yc, xs, ys);
+            accumulate_run_smem<MATH, false>(tile[2], a2 - sA2, b2 - sA2, 0, me.x, me.y, xa, ya, xc, yc, xs, ys);
+        }
         acc.xa = xa; acc.ya = ya; acc.xc = xc; acc.yc = yc; acc.xs = xs; acc.ys = ys;
         acc.nvec = (b0 - a0) + (b1 - a1) + (b2 - a2);
         acc.count = (int)acc.nvec - 1;
@@ -504,6 +557,30 @@ void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id
                    const float2 *ld, const uint32_t *payload, uint32_t base, int owned_only, cudaStream_t st) {
     if (n == 0) return;
     k_ingest<<<(n + 255) / 256, 256, 0, st>>>(g, s, n, id, loc, ld, payload, base, owned_only);
+}
+
+// dense form: the host keeps its agents as a list indexed by id (Flocker::init numbers them 0..N in list order,
+// flockers/src/model/state.rs:40-51), so the id is the position and one 16-byte {loc, last_d} record is all that moves
+__global__ void __launch_bounds__(256) k_ingest_dense(const Geom g, const Store s, uint32_t n, uint32_t id0,
+                                                      const float4 *__restrict__ rec4, uint32_t base) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float4 r = rec4[j];
+    const int cx = cell_coord(r.x, g.d, g.mx + 1);
+    const int cy = cell_coord(r.y, g.d, g.dh);
+    const uint32_t key = (uint32_t)cx * (uint32_t)g.dh + (uint32_t)cy;
+    const uint32_t slot = atomicAdd(s.cnt + key, 1u);
+    reinterpret_cast<float4 *>(s.trec)[base + j] = r;
+    s.tid[base + j] = id0 + j;
+    s.tkey[base + j] = key;
+    s.tslot[base + j] = slot;
+    for (uint32_t k = 0; k < s.pw; ++k) s.tpay[(size_t)(base + j) * s.pw + k] = 0u;
+}
+
+void launch_ingest_dense(const Geom &g, const Store &s, uint32_t n, uint32_t id0, const float4 *rec4, uint32_t base,
+                         cudaStream_t st) {
+    if (n == 0) return;
+    k_ingest_dense<<<(n + 255) / 256, 256, 0, st>>>(g, s, n, id0, rec4, base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -825,6 +902,22 @@ __global__ void __launch_bounds__(256) k_split(const Store s, uint32_t n, float2
 void launch_split(const Store &s, uint32_t n, float2 *loc, float2 *ld, cudaStream_t st) {
     if (n == 0) return;
     k_split<<<(n + 255) / 256, 256, 0, st>>>(s, n, loc, ld);
+}
+
+// dense snapshot: READ record of object `id` -> out[id - id0] (ids outside [id0, id0+n) are counted, not written)
+__global__ void __launch_bounds__(256) k_gather_dense(const Store s, uint32_t n_upper, uint32_t id0, uint32_t n,
+                                                      float4 *__restrict__ out, uint32_t *__restrict__ outside) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_upper || i >= *s.n_read_dev) return;
+    const uint32_t k = s.ids[i] - id0;
+    if (k < n) out[k] = reinterpret_cast<const float4 *>(s.rec)[i];
+    else atomicAdd(outside, 1u);
+}
+
+void launch_gather_dense(const Store &s, uint32_t n_upper, uint32_t id0, uint32_t n, float4 *out, uint32_t *outside,
+                         cudaStream_t st) {
+    if (n_upper == 0) return;
+    k_gather_dense<<<(n_upper + 255) / 256, 256, 0, st>>>(s, n_upper, id0, n, out, outside);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -58,6 +58,10 @@ struct StepArgs {
 
 void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id, const float2 *loc,
                    const float2 *ld, const uint32_t *payload, uint32_t base, int owned_only, cudaStream_t st);
+void launch_ingest_dense(const Geom &g, const Store &s, uint32_t n, uint32_t id0, const float4 *rec4, uint32_t base,
+                         cudaStream_t st);
+void launch_gather_dense(const Store &s, uint32_t n_upper, uint32_t id0, uint32_t n, float4 *out, uint32_t *outside,
+                         cudaStream_t st);
 void launch_unpack(const Geom &g, const Store &s, cudaStream_t st);
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st);

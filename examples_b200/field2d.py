@@ -232,6 +232,26 @@ class Field2D:
         check(self._L.flk_snapshot(self._h, C.c_void_p(id_ptr), C.c_void_p(loc_ptr), C.c_void_p(ld_ptr), C.byref(cnt)))
         return cnt.value
 
+    # ---- dense (id-indexed) host interface: 16 bytes per object each way
+    def set_objects_dense(self, rec4: np.ndarray, id0: int = 0):
+        """set_object_location for ids id0..id0+n-1; rec4[k] = (loc.x, loc.y, last_d.x, last_d.y) of object id0+k"""
+        rec4 = np.ascontiguousarray(rec4, dtype=np.float32)
+        assert rec4.size % 4 == 0
+        check(self._L.flk_set_objects_dense(self._h, rec4.size // 4, id0, _vp(rec4)))
+
+    def snapshot_dense(self, n: int, id0: int = 0) -> np.ndarray:
+        """rec4[n,4] indexed by id - id0 (NaN rows for ids the field does not hold)"""
+        out = np.zeros((n, 4), dtype=np.float32)
+        check(self._L.flk_snapshot_dense(self._h, id0, n, _vp(out)))
+        return out
+
+    def set_objects_dense_raw(self, n: int, ptr: int, id0: int = 0):
+        check(self._L.flk_set_objects_dense(self._h, n, id0, C.c_void_p(ptr)))
+
+    def snapshot_dense_async_raw(self, n: int, ptr: int, id0: int = 0):
+        """enqueue only; call synchronize() before reading the (pinned) buffer"""
+        check(self._L.flk_snapshot_dense_async(self._h, id0, n, C.c_void_p(ptr)))
+
     def snapshot_by_id(self):
         ids, loc, ld = self.snapshot()
         o = np.argsort(ids, kind="stable")

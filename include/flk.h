@@ -129,6 +129,22 @@ int flk_snapshot(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t
  * *found = 0 when no object has that id (the reference returns None); out = {x, y, last_d.x, last_d.y}. */
 int flk_get_object(flk_field *f, uint32_t id, float out[4], int32_t *found);
 
+/* flk_snapshot without the final synchronisation: returns once the copies are enqueued on the handle's stream.
+ * The HOST arrays must be pinned (flk_host_alloc) and must not be read before flk_synchronize returns. */
+int flk_snapshot_async(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n);
+
+/* Dense host interface.  The reference's host copy of the agents is a list indexed by id: Flocker::init numbers the
+ * birds 0..N in list order (flockers/src/model/state.rs:40-51) and Bird is hashed by id alone (bird.rs:148-163).
+ * With the id implied by the position only Bird's 16 bytes {loc.x, loc.y, last_d.x, last_d.y} move per object.
+ *   flk_set_objects_dense   set_object_location for ids id0 .. id0+n-1, rec4[4*k..4*k+3] = object id0+k
+ *   flk_snapshot_dense      rec4[4*k..] = READ copy of object id0+k (all-ones NaN when no such object);
+ *                           FLK_E_INVALID if the field holds an id outside [id0, id0+n)
+ *   ..._async               as flk_snapshot_async; the range check is reported by the next flk_synchronize
+ * Single-GPU handles only (a strip owns an arbitrary subset of the ids). */
+int flk_set_objects_dense(flk_field *f, uint64_t n, uint32_t id0, const float *rec4);
+int flk_snapshot_dense(flk_field *f, uint32_t id0, uint64_t n, float *rec4);
+int flk_snapshot_dense_async(flk_field *f, uint32_t id0, uint64_t n, float *rec4);
+
 /* flk_snapshot plus the payload bytes, same order */
 int flk_snapshot_ex(flk_field *f, uint32_t *id, float *loc, float *last_d, void *payload, uint64_t *n);
 
