@@ -187,10 +187,12 @@ __device__ __forceinline__ void xbuf_append(const Store &s, uint8_t *buf, const 
     }
 }
 
+template <bool NOPAY = false>
 __device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, const Rec &out, uint32_t id, uint32_t w,
                                                bool d_ok, const Recip &Rd, uint32_t src) {
     // Field2D<O>: whatever else the object carries moves with it (set_object_location stores the whole object)
-    for (uint32_t k = 0; k < s.pw; ++k) s.tpay[(size_t)w * s.pw + k] = s.pay[(size_t)src * s.pw + k];
+    if (!NOPAY)
+        for (uint32_t k = 0; k < s.pw; ++k) s.tpay[(size_t)w * s.pw + k] = s.pay[(size_t)src * s.pw + k];
     const int ncx = d_ok ? cell_coord_fast(out.x, Rd, g.mx + 1) : cell_coord(out.x, g.d, g.mx + 1);
     const int ncy = d_ok ? cell_coord_fast(out.y, Rd, g.dh) : cell_coord(out.y, g.d, g.dh);
     const int nlc = local_col(g, ncx);
@@ -236,7 +238,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 constexpr int TILE_CAP = 256;   // records staged per window column (4 KB); 3 columns = 12 KB per CTA
 
 // everything of Bird::step after the neighbour loop (bird.rs:73-145) + set_object_location
-template <int MATH>
+template <int MATH, bool NOPAY = false>
 __device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, const Store &s, const StepArgs &a, const Rec &me,
                                             uint32_t my_id, uint32_t w, const Acc &acc, bool d_ok, const Recip &Rd,
                                             uint32_t src) {
@@ -308,7 +310,7 @@ __device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, cons
     out.x = toroidal_transform(__fadd_rn(me.x, dx), W);                              // :137
     out.y = toroidal_transform(__fadd_rn(me.y, dy), H);                              // :138
 
-    emit_successor(g, s, out, my_id, w, d_ok, Rd, src);   // :142-144
+    emit_successor<NOPAY>(g, s, out, my_id, w, d_ok, Rd, src);   // :142-144
 }
 
 // interior accumulation out of the CTA's shared-memory tile (same order, same arithmetic as accumulate_interior)
@@ -334,32 +336,63 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 
+// FLK_PACKMASK selects which groups of the loop use the two-lane form (bit 0: difference and squares, bit 1: the two
+// quotients, bit 2: the three accumulator pairs).  A two-lane instruction occupies the FMA pipe for ~2.3 cycles against
+// 2 x 1.05 for its scalar pair (tools/micro/x2_throughput.cu), so packing only pays where issue slots are the limit.
+#ifndef FLK_PACKMASK
+#define FLK_PACKMASK 7
+#endif
 template <bool SELF>
 __device__ __forceinline__ void accumulate_run_smem_packed(const float4 *tile, uint32_t j, uint32_t e, uint32_t self,
                                                            f32x2 ME, f32x2 &A, f32x2 &Cc, f32x2 &Ss) {
     const ulonglong2 *t2 = reinterpret_cast<const ulonglong2 *>(tile);
     const f32x2 NEG1 = pk(-1.0f, -1.0f);
+    float mx_, my_;
+    unpk(ME, mx_, my_);
 #pragma unroll kSmemUnroll
     for (; j < e; ++j) {
         ulonglong2 o = t2[j];
         if (SELF && j == self) o.y = 0ull;                     // (last_d) := (+0,+0), see accumulate_run_smem
-        const f32x2 Dv = fma2(o.x, NEG1, ME);                   // bird.rs:54-55 (no seam in reach)
-        const f32x2 Sv = mul2(Dv, Dv);
-        float s0, s1;
-        unpk(Sv, s0, s1);
+        f32x2 Dv;
+        float dx, dy, s0, s1;
+        if (FLK_PACKMASK & 1) {
+            Dv = fma2(o.x, NEG1, ME);                           // bird.rs:54-55 (no seam in reach)
+            unpk(Dv, dx, dy);
+            unpk(mul2(Dv, Dv), s0, s1);
+        } else {
+            float ox, oy;
+            unpk(o.x, ox, oy);
+            dx = __fadd_rn(mx_, -ox); dy = __fadd_rn(my_, -oy);
+            Dv = pk(dx, dy);
+            s0 = __fmul_rn(dx, dx); s1 = __fmul_rn(dy, dy);
+        }
         const float sq = __fadd_rn(s0, s1);                    // :59
         const float nden = __fadd_rn(-__fmul_rn(sq, sq), -1.0f);
         float r;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-nden));
         const float er = __fmaf_rn(nden, r, 1.0f);             // div2_rn_interior, two lanes at a time
         r = __fmaf_rn(r, er, r);
-        const f32x2 RR = pk(r, r), ND = pk(nden, nden);
-        const f32x2 Q0 = mul2(Dv, RR);
-        const f32x2 REM = fma2(ND, Q0, Dv);
-        const f32x2 Q = fma2(RR, REM, Q0);                      // :60-61
-        A = add2(A, Q);
-        Cc = add2(Cc, Dv);                                      // :64-65
-        Ss = add2(Ss, o.y);                                     // :68-69
+        f32x2 Q;
+        if (FLK_PACKMASK & 2) {
+            const f32x2 RR = pk(r, r), ND = pk(nden, nden);
+            const f32x2 Q0 = mul2(Dv, RR);
+            const f32x2 REM = fma2(ND, Q0, Dv);
+            Q = fma2(RR, REM, Q0);                              // :60-61
+        } else {
+            const float q0 = __fmul_rn(dx, r), q1 = __fmul_rn(dy, r);
+            const float rem0 = __fmaf_rn(nden, q0, dx), rem1 = __fmaf_rn(nden, q1, dy);
+            Q = pk(__fmaf_rn(r, rem0, q0), __fmaf_rn(r, rem1, q1));
+        }
+        if (FLK_PACKMASK & 4) {
+            A = add2(A, Q);
+            Cc = add2(Cc, Dv);                                  // :64-65
+            Ss = add2(Ss, o.y);                                 // :68-69
+        } else {
+            float a0, a1, q0, q1;
+            unpk(A, a0, a1); unpk(Q, q0, q1); A = pk(__fadd_rn(a0, q0), __fadd_rn(a1, q1));
+            unpk(Cc, a0, a1); Cc = pk(__fadd_rn(a0, dx), __fadd_rn(a1, dy));
+            unpk(Ss, a0, a1); unpk(o.y, q0, q1); Ss = pk(__fadd_rn(a0, q0), __fadd_rn(a1, q1));
+        }
     }
 }
 
@@ -393,43 +426,71 @@ __device__ __forceinline__ void accumulate_run_smem(const float4 *tile, uint32_t
     }
 }
 
+// Everything that is not the common case — a bird next to the seam, a CTA that straddles two cell columns, a window
+// wider than 3x3, the exact-distance query, a non-toroidal field — finishes its bird here.  Kept out of line so
+// that the register allocation of the tile path in k_step is not shaped by these loops (same arithmetic, same order).
+template <bool RELAX, int MATH>
+__device__ __noinline__ void step_bird_general(const Geom &g, const Params &p, const Store &s, const StepArgs &a,
+                                               uint32_t i, uint32_t w) {
+    const Rec me = s.rec[i];
+    const uint32_t my_id = s.ids[i];
+    const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
+    const Recip Rd = make_recip(g.d);
+    const int gcx = d_ok ? cell_coord_fast(me.x, Rd, g.mx + 1) : cell_coord(me.x, g.d, g.mx + 1);
+    const int cy = d_ok ? cell_coord_fast(me.y, Rd, g.dh) : cell_coord(me.y, g.d, g.dh);
+    const int lc = local_col(g, gcx);
+    Acc acc;
+    // Birds whose 3x3 window cannot touch the seam never take the |a-b| > dim/2 branch of toroidal_distance:
+    // cells are < 2d apart and dim >= 6d, so the plain difference is the toroidal one (exactly).
+    const bool interior = g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && gcx >= 1 && gcx <= g.mx - 2 &&
+                          cy >= 1 && cy <= g.my - 2 && d_ok;
+    if (interior && RELAX) accumulate_interior<MATH>(g, s, me, i, lc, cy, acc);
+    else accumulate_window<RELAX, MATH>(g, p, s, me, i, lc, cy, acc);
+    finish_bird<MATH>(g, p, s, a, me, my_id, w, acc, d_ok, Rd, i);
+}
+
 // k_step: one thread per READ bird.  TILE = stage the CTA's three window-column runs in shared memory with TMA bulk
-// copies when the CTA's birds sit in one interior column (the common case); other CTAs read through L1.
+// copies when the CTA's birds sit in one interior column (the common case); other CTAs take step_bird_general.
+// FASTG = the host checked what does not depend on the bird (launch_step): toroidal field, 3x3 window, relax query,
+// grid >= 6x6 cells, discretisation in the shared-reciprocal range, no payload, not the identity pass.
 #ifndef FLK_STEP_MINBLOCKS
 #define FLK_STEP_MINBLOCKS 12
 #endif
-template <bool RELAX, int MATH, bool TILE>
-__global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS) k_step(const Geom g, const Params p, const Store s, const StepArgs a) {
+template <bool RELAX, int MATH, bool TILE, bool FASTG>
+__global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS)
+k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const __grid_constant__ Store s,
+       const __grid_constant__ StepArgs a) {
     __shared__ __align__(128) float4 tile[TILE ? 3 : 1][TILE ? TILE_CAP : 1];
     __shared__ __align__(8) uint64_t bar;
     __shared__ int shc[5];
 
-    const uint32_t lo = __ldg(s.cell_start + a.cell_lo);
-    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
+    // cell_start[0] is 0 by construction: a whole-field launch knows its first bird without a load, so the bird's own
+    // record (read speculatively: any index below cap is allocated) is in flight together with the range end
+    const uint32_t lo = a.cell_lo ? __ldg(s.cell_start + a.cell_lo) : 0u;
     const uint32_t first = lo + blockIdx.x * blockDim.x;
+    const uint32_t i = first + threadIdx.x;
+    float2 xy = make_float2(0.0f, 0.0f);
+    if (TILE && i < s.cap) xy = *reinterpret_cast<const float2 *>(s.rec + i);
+    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
     if (blockIdx.x == 0 && threadIdx.x == 0 && hi - lo > gridDim.x * blockDim.x)
         atomicOr(s.err_flag, ERR_EXCHANGE);        // the launch does not cover the range (border launches use capx)
     if (first >= hi) return;                       // whole CTA out of range
-    const uint32_t i = first + threadIdx.x;
     const bool valid = i < hi;
+    const uint32_t w = a.out_base + i;
 
-    Rec me = Rec{0.f, 0.f, 0.f, 0.f};
-    uint32_t my_id = 0;
-    // cell of this bird (same arithmetic as the binning that placed it)
-    const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
-    const Recip Rd = make_recip(g.d);
-    int gcx = 0, cy = 0, lc = 0;
-    if (valid) {
-        me = s.rec[i];
-        my_id = s.ids[i];
-        gcx = d_ok ? cell_coord_fast(me.x, Rd, g.mx + 1) : cell_coord(me.x, g.d, g.mx + 1);
-        cy = d_ok ? cell_coord_fast(me.y, Rd, g.dh) : cell_coord(me.y, g.d, g.dh);
-        lc = local_col(g, gcx);
-    }
-
-    bool use_tile = false;
-    uint32_t sA0 = 0, sA1 = 0, sA2 = 0;
     if (TILE) {
+        // cell of this bird (same arithmetic as the binning that placed it)
+        const bool d_ok = FASTG || (g.d >= 0x1p-20f && g.d <= 4096.0f);
+        const Recip Rd = make_recip(g.d);
+        const uint32_t dh = (uint32_t)g.dh;
+        float mex = 0.0f, mey = 0.0f;
+        int gcx = 0, cy = 0, lc = 0;
+        if (valid) {
+            mex = xy.x; mey = xy.y;
+            gcx = d_ok ? cell_coord_fast(mex, Rd, g.mx + 1) : cell_coord(mex, g.d, g.mx + 1);
+            cy = d_ok ? cell_coord_fast(mey, Rd, g.dh) : cell_coord(mey, g.d, g.dh);
+            lc = local_col(g, gcx);
+        }
         const uint32_t last = min(first + blockDim.x, hi) - 1;
         if (threadIdx.x == 0) {
             shc[0] = lc; shc[1] = cy; shc[4] = gcx;
@@ -438,15 +499,17 @@ __global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS) k_step(const Geom g, 
         if (i == last) { shc[2] = lc; shc[3] = cy; }
         __syncthreads();
         const int lcA = shc[0], cyA = shc[1], lcB = shc[2], cyB = shc[3], gcxA = shc[4];
-        bool eligible = RELAX && !a.identity && g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && d_ok &&
+        bool eligible = (FASTG || (RELAX && !a.identity && g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && d_ok &&
+                                   s.pw == 0)) &&
                         lcA == lcB && gcxA >= 1 && gcxA <= g.mx - 2 && cyA >= 1 && cyB <= g.my - 2 && cyA <= cyB &&
                         (g.mode == 0 || (lcA >= 1 && lcA <= g.nown));
-        uint32_t len0 = 0, len1 = 0, len2 = 0;
+        uint32_t sA0 = 0, sA1 = 0, sA2 = 0, len0 = 0, len1 = 0, len2 = 0;
         if (eligible) {
-            const uint32_t *cs = s.cell_start + (uint32_t)(lcA - 1) * (uint32_t)g.dh;
-            sA0 = __ldg(cs + cyA - 1);            len0 = __ldg(cs + cyB + 2) - sA0;
-            sA1 = __ldg(cs + g.dh + cyA - 1);     len1 = __ldg(cs + g.dh + cyB + 2) - sA1;
-            sA2 = __ldg(cs + 2 * g.dh + cyA - 1); len2 = __ldg(cs + 2 * g.dh + cyB + 2) - sA2;
+            const uint32_t *cs = s.cell_start + ((uint32_t)(lcA - 1) * dh + (uint32_t)(cyA - 1));
+            const uint32_t span = (uint32_t)(cyB - cyA) + 3u;
+            sA0 = __ldg(cs);          len0 = __ldg(cs + span) - sA0;
+            sA1 = __ldg(cs + dh);     len1 = __ldg(cs + dh + span) - sA1;
+            sA2 = __ldg(cs + 2 * dh); len2 = __ldg(cs + 2 * dh + span) - sA2;
             eligible = len0 <= TILE_CAP && len1 <= TILE_CAP && len2 <= TILE_CAP;
         }
         if (eligible) {   // CTA-uniform
@@ -457,55 +520,58 @@ __global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS) k_step(const Geom g, 
                 if (len1) tma_load_1d(&tile[1][0], rec + sA1, len1 * 16u, &bar);
                 if (len2) tma_load_1d(&tile[2][0], rec + sA2, len2 * 16u, &bar);
             }
+            // this bird's three runs, as offsets into the staged column runs (loads in flight during the copy)
+            uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+            if (valid) {
+                const uint32_t *cs = s.cell_start + ((uint32_t)(lc - 1) * dh + (uint32_t)(cy - 1));
+                a0 = __ldg(cs);          b0 = __ldg(cs + 3);
+                a1 = __ldg(cs + dh);     b1 = __ldg(cs + dh + 3);
+                a2 = __ldg(cs + 2 * dh); b2 = __ldg(cs + 2 * dh + 3);
+            }
             mbar_wait(&bar, 0);
-            use_tile = true;
+            if (!valid) return;
+            float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
+            if (MATH == 0 && FLK_PACKED) {
+                const f32x2 ME = pk(mex, mey);
+                f32x2 A = 0ull, Cc = 0ull, Ss = 0ull;
+                accumulate_run_smem_packed<false>(tile[0], a0 - sA0, b0 - sA0, 0, ME, A, Cc, Ss);
+                accumulate_run_smem_packed<true>(tile[1], a1 - sA1, b1 - sA1, i - sA1, ME, A, Cc, Ss);
+                accumulate_run_smem_packed<false>(tile[2], a2 - sA2, b2 - sA2, 0, ME, A, Cc, Ss);
+                unpk(A, xa, ya); unpk(Cc, xc, yc); unpk(Ss, xs, ys);
+            } else {
+                accumulate_run_smem<MATH, false>(tile[0], a0 - sA0, b0 - sA0, 0, mex, mey, xa, ya, xc, yc, xs, ys);
+                accumulate_run_smem<MATH, true>(tile[1], a1 - sA1, b1 - sA1, i - sA1, mex, mey, xa, ya, xc, yc, xs, ys);
+                accumulate_run_smem<MATH, false>(tile[2], a2 - sA2, b2 - sA2, 0, mex, mey, xa, ya, xc, yc, xs, ys);
+            }
+            Acc acc;
+            acc.xa = xa; acc.ya = ya; acc.xc = xc; acc.yc = yc; acc.xs = xs; acc.ys = ys;
+            acc.nvec = (b0 - a0) + (b1 - a1) + (b2 - a2);
+            acc.count = (int)acc.nvec - 1;
+            // the heading and the id are only needed from here on: fetched now (L1/L2 hits) instead of being carried
+            // through the loops
+            const float2 ld = *(reinterpret_cast<const float2 *>(s.rec + i) + 1);
+            const Rec me = Rec{mex, mey, ld.x, ld.y};
+            finish_bird<MATH, FASTG>(g, p, s, a, me, s.ids[i], w, acc, d_ok, Rd, i);
+            return;
         }
     }
     if (!valid) return;
-
-    const uint32_t w = a.out_base + i;
-    if (g.mode == 1 && (lc == 0 || lc == g.nown + 1)) {
-        // ghost copy (flockers_mpi: received_neighbors): stepped by its owner, dropped here
-        s.tkey[w] = KEY_INVALID;
-        return;
+    if (g.mode == 1) {
+        const Rec me = s.rec[i];
+        const int gcx = cell_coord(me.x, g.d, g.mx + 1);
+        const int lc = local_col(g, gcx);
+        if (lc == 0 || lc == g.nown + 1) {
+            // ghost copy (flockers_mpi: received_neighbors): stepped by its owner, dropped here
+            s.tkey[w] = KEY_INVALID;
+            return;
+        }
     }
     if (a.identity) {
-        emit_successor(g, s, me, my_id, w, d_ok, Rd, i);
+        const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
+        emit_successor(g, s, s.rec[i], s.ids[i], w, d_ok, make_recip(g.d), i);
         return;
     }
-
-    Acc acc;
-    if (TILE && use_tile) {
-        // this bird's three runs, as offsets into the staged column runs
-        const uint32_t *cs = s.cell_start + (uint32_t)(lc - 1) * (uint32_t)g.dh + (uint32_t)(cy - 1);
-        const uint32_t a0 = __ldg(cs), b0 = __ldg(cs + 3);
-        const uint32_t a1 = __ldg(cs + g.dh), b1 = __ldg(cs + g.dh + 3);
-        const uint32_t a2 = __ldg(cs + 2 * g.dh), b2 = __ldg(cs + 2 * g.dh + 3);
-        float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
-        if (MATH == 0 && FLK_PACKED) {
-            const f32x2 ME = pk(me.x, me.y);
-            f32x2 A = 0ull, Cc = 0ull, Ss = 0ull;
-            accumulate_run_smem_packed<false>(tile[0], a0 - sA0, b0 - sA0, 0, ME, A, Cc, Ss);
-            accumulate_run_smem_packed<true>(tile[1], a1 - sA1, b1 - sA1, i - sA1, ME, A, Cc, Ss);
-            accumulate_run_smem_packed<false>(tile[2], a2 - sA2, b2 - sA2, 0, ME, A, Cc, Ss);
-            unpk(A, xa, ya); unpk(Cc, xc, yc); unpk(Ss, xs, ys);
-        } else {
-            accumulate_run_smem<MATH, false>(tile[0], a0 - sA0, b0 - sA0, 0, me.x, me.y, xa, ya, xc, yc, xs, ys);
-            accumulate_run_smem<MATH, true>(tile[1], a1 - sA1, b1 - sA1, i - sA1, me.x, me.y, xa, ya, xc, yc, xs, ys);
-            accumulate_run_smem<MATH, false>(tile[2], a2 - sA2, b2 - sA2, 0, me.x, me.y, xa, ya, xc, yc, xs, ys);
-        }
-        acc.xa = xa; acc.ya = ya; acc.xc = xc; acc.yc = yc; acc.xs = xs; acc.ys = ys;
-        acc.nvec = (b0 - a0) + (b1 - a1) + (b2 - a2);
-        acc.count = (int)acc.nvec - 1;
-    } else {
-        // Birds whose 3x3 window cannot touch the seam never take the |a-b| > dim/2 branch of toroidal_distance:
-        // cells are < 2d apart and dim >= 6d, so the plain difference is the toroidal one (exactly).
-        const bool interior = g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && gcx >= 1 && gcx <= g.mx - 2 &&
-                              cy >= 1 && cy <= g.my - 2 && d_ok;
-        if (interior && RELAX) accumulate_interior<MATH>(g, s, me, i, lc, cy, acc);
-        else accumulate_window<RELAX, MATH>(g, p, s, me, i, lc, cy, acc);
-    }
-    finish_bird<MATH>(g, p, s, a, me, my_id, w, acc, d_ok, Rd, i);
+    step_bird_general<RELAX, MATH>(g, p, s, a, i, w);
 }
 
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
@@ -514,13 +580,22 @@ void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs 
     static const int tile = [] { const char *e = getenv("FLK_STEP_TILE"); return e ? atoi(e) : 1; }();
     const int bs = 128;
     const dim3 block(bs), grid((n_upper + bs - 1) / bs);
-#define FLK_LAUNCH(R, M, T) k_step<R, M, T><<<grid, block, 0, st>>>(g, p, s, a)
+    const bool fastg = p.relax && g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && g.d >= 0x1p-20f && g.d <= 4096.0f &&
+                       s.pw == 0 && !a.identity;
+#define FLK_LAUNCH(R, M, T, F) k_step<R, M, T, F><<<grid, block, 0, st>>>(g, p, s, a)
     if (p.relax) {
-        if (a.math_mode == 1) { if (tile) FLK_LAUNCH(true, 1, true); else FLK_LAUNCH(true, 1, false); }
-        else { if (tile) FLK_LAUNCH(true, 0, true); else FLK_LAUNCH(true, 0, false); }
+        if (a.math_mode == 1) {
+            if (tile && fastg) FLK_LAUNCH(true, 1, true, true);
+            else if (tile) FLK_LAUNCH(true, 1, true, false);
+            else FLK_LAUNCH(true, 1, false, false);
+        } else {
+            if (tile && fastg) FLK_LAUNCH(true, 0, true, true);
+            else if (tile) FLK_LAUNCH(true, 0, true, false);
+            else FLK_LAUNCH(true, 0, false, false);
+        }
     } else {
-        if (a.math_mode == 1) FLK_LAUNCH(false, 1, false);
-        else FLK_LAUNCH(false, 0, false);
+        if (a.math_mode == 1) FLK_LAUNCH(false, 1, false, false);
+        else FLK_LAUNCH(false, 0, false, false);
     }
 #undef FLK_LAUNCH
 }
