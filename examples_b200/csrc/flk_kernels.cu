@@ -454,7 +454,7 @@ __device__ __noinline__ void step_bird_general(const Geom &g, const Params &p, c
 // FASTG = the host checked what does not depend on the bird (launch_step): toroidal field, 3x3 window, relax query,
 // grid >= 6x6 cells, discretisation in the shared-reciprocal range, no payload, not the identity pass.
 #ifndef FLK_STEP_MINBLOCKS
-#define FLK_STEP_MINBLOCKS 12
+#define FLK_STEP_MINBLOCKS 10   // 48 registers; measured 0.858-0.867 ms against 0.872-0.876 (12), 0.885 (13-16), 0.925 (8)
 #endif
 template <bool RELAX, int MATH, bool TILE, bool FASTG>
 __global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS)

@@ -65,6 +65,15 @@ public:
         check(flk_num_objects(h_, &n));
         return n;
     }
+    // the agents as the Schedule keeps them, a list indexed by id (state.rs:40-51): 16 bytes per bird each way
+    void set_all_dense(const std::vector<float> &rec4) {
+        check(flk_set_objects_dense(h_, rec4.size() / 4, 0, rec4.data()));
+    }
+    std::vector<float> get_all_dense(size_t n) {
+        std::vector<float> rec4(4 * n);
+        check(flk_snapshot_dense(h_, 0, n, rec4.data()));
+        return rec4;
+    }
     std::vector<Bird> get_all() {   // Field2D::get / get_location for every object (vis_state.rs:52)
         const uint64_t n = num_objects();
         std::vector<uint32_t> id(n);
