@@ -150,7 +150,7 @@ int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc,
 
 int enqueue_lazy_update(flk_field *f, int bump_step) {
     const uint32_t m = f->ncell + 1;
-    const bool prof = f->profile && !f->capturing;
+    const bool prof = f->profile && f->profile_level >= 2 && !f->capturing;
     auto mark = [&]() -> int {
         if (!prof) return FLK_OK;
         cudaEvent_t e;
@@ -640,6 +640,7 @@ int flk_profile_enable(flk_field *f, int on) {
     for (auto &e : f->prof_rebin) cudaEventDestroy(e);
     f->prof_rebin.clear();
     f->profile = on != 0;
+    f->profile_level = on;   // 1 = events around k_step only; 2 = also around the three lazy_update phases
     return FLK_OK;
 }
 

@@ -35,6 +35,7 @@ struct flk_field {
     uint64_t graph_n = 0, graph_seed = 0, graph_launches = 0;
     uint64_t launches = 0;
     bool profile = false;
+    int profile_level = 0;
     std::vector<cudaEvent_t> prof_events;      // pairs around every k_step launch (set)
     std::vector<cudaEvent_t> prof_rebin;       // quadruples per lazy_update: start, after scan, after scatter, after rank
     flk_dist_state *dist = nullptr;

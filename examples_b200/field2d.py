@@ -277,7 +277,8 @@ class Field2D:
         check(self._L.flk_launch_count(self._h, C.byref(n)))
         return n.value
 
-    def profile_enable(self, on: bool):
+    def profile_enable(self, on):
+        """1/True: events around each k_step launch; 2: also around the lazy_update phases; 0/False: off"""
         check(self._L.flk_profile_enable(self._h, int(on)))
 
     def profile_rebin(self):

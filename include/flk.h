@@ -159,7 +159,8 @@ int flk_elapsed_ms(flk_field *f, float *ms);
 int flk_stream(flk_field *f, void **stream);
 /* kernels launched by this handle since creation */
 int flk_launch_count(const flk_field *f, uint64_t *n);
-/* average device time (ms) and launches of the step kernel since flk_profile_reset; CUDA events around each launch */
+/* on = 1: CUDA events around every step-kernel launch (flk_profile_step_kernel); on = 2: also around the three
+ * lazy_update phases (flk_profile_rebin); 0 = off.  While on, flk_run launches directly instead of replaying its graph. */
 int flk_profile_enable(flk_field *f, int on);
 /* flk_run replays a captured CUDA graph per tick (default on); off = plain launches */
 int flk_use_graph(flk_field *f, int on);

@@ -15,7 +15,7 @@ if os.environ.get("AB_CHILD"):
     f = Field2D(W, H, bench.D, True, capacity=n)
     f.set_objects(np.arange(n, dtype=np.uint32), loc, np.zeros_like(loc)); f.lazy_update()
     f.run(0, 10); f.synchronize()
-    f.profile_enable(True)
+    f.profile_enable(2)
     f.run(10, ticks); f.synchronize()
     ms = f.elapsed_ms(); k_ms, k_n = f.profile_step_kernel(); rb = f.profile_rebin()
     f.profile_enable(False)
