@@ -348,29 +348,63 @@ def run_ours(args, world: int, rank: int, local_rank: int):
                              "flk_snapshot_dense_async(pinned host, 16 B/bird); output feeds the next step's input; "
                              "serial_value = one repetition alone (no overlap)"}
     else:
-        o_id = torch.empty_like(h_id).pin_memory()      # empty_like of a pinned tensor is pageable: pin explicitly
-        o_loc = torch.empty_like(h_loc).pin_memory()
-        o_ld = torch.empty_like(h_ld).pin_memory()
-        assert o_id.is_pinned() and o_loc.is_pinned() and o_ld.is_pinned() and h_id.is_pinned() and h_loc.is_pinned()
-        for it in range(e2e_steps + 1):
-            if it == 1:
-                barrier()
-                t0 = time.perf_counter()
-            f.set_objects_raw(n_local, h_id.data_ptr(), h_loc.data_ptr(), h_ld.data_ptr())
-            f.commit()
-            f.run(1000 + it, 1, STEP_SEED)
-            got = f.snapshot_owned_raw(o_id.data_ptr(), o_loc.data_ptr(), o_ld.data_ptr())
-            # the host keeps the agents: next step's input is this step's output (ids follow the records)
-            h_id, o_id = o_id, h_id
-            h_loc, o_loc = o_loc, h_loc
-            h_ld, o_ld = o_ld, h_ld
-            n_local = got
-        barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
-        e2e_value = n_total * e2e_steps / e2e_s
+        # One strip per rank: the birds a rank owns change with migration, so ids travel with the records (20 B per
+        # bird each way).  `reps` independent repetitions, each its own group of strip handles (own NCCL communicator),
+        # are pipelined like the single-GPU case; every rank walks the repetitions in the same order (collectives).
+        reps = max(1, args.e2e_reps)
+        cap_h = n_local + n_local // 8 + 65536
+
+        def e2e_run_dist(fields, steps):
+            R = len(fields)
+            bufs = []
+            for r in range(R):
+                pair = []
+                for _ in range(2):
+                    pair.append((torch.empty(cap_h, dtype=torch.int32).pin_memory(),
+                                 torch.empty((cap_h, 2), dtype=torch.float32).pin_memory(),
+                                 torch.empty((cap_h, 2), dtype=torch.float32).pin_memory()))
+                pair[0][0][:n_local].copy_(torch.from_numpy(np.arange(id_base, id_base + n_local, dtype=np.uint32).view(np.int32)))
+                pair[0][1][:n_local].copy_(torch.from_numpy(loc))
+                pair[0][2][:n_local].zero_()
+                bufs.append(pair)
+            counts = [n_local] * R
+            t0 = 0.0
+            for it in range(steps + 1):
+                if it == 1:
+                    for fr in fields:
+                        fr.synchronize()
+                    barrier()
+                    t0 = time.perf_counter()
+                for r, fr in enumerate(fields):
+                    fr.synchronize()
+                    (i_id, i_loc, i_ld), (o_id, o_loc, o_ld) = bufs[r]
+                    fr.set_objects_raw(counts[r], i_id.data_ptr(), i_loc.data_ptr(), i_ld.data_ptr())
+                    fr.commit()
+                    fr.run(1000 + it, 1, STEP_SEED + r)
+                    counts[r] = fr.snapshot_owned_async_raw(o_id.data_ptr(), o_loc.data_ptr(), o_ld.data_ptr())
+                    assert counts[r] <= cap_h, (counts[r], cap_h)
+                    bufs[r] = [bufs[r][1], bufs[r][0]]
+            for fr in fields:
+                fr.synchronize()
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            total = sum_over_ranks(float(sum(counts)))
+            assert int(total) == R * n_total, (total, R * n_total)
+            return R * n_total * steps / dt
+
+        extra = [fdist.DistField2D(W, H, D, capacity=cap, device=local_rank, rank=rank, world=world) for _ in range(reps - 1)]
+        for fx in extra:
+            fx.set_math_mode(args.math)
+        serial_value = e2e_run_dist([f], e2e_steps)
+        e2e_value = e2e_run_dist([f] + extra, e2e_steps)
+        for fx in extra:
+            fx.close()
         e2e_bytes = 20 * (n_total // world)
-        e2e_extra = {"what": "per rank: flk_set_objects(host) + commit + Bird::step + exchange + lazy_update + "
-                             "flk_dist_snapshot_owned(host) per step, 20 B/bird each way"}
+        e2e_extra = {"reps": reps, "serial_value": serial_value,
+                     "what": f"{reps} independent repetitions pipelined over {reps} groups of strip handles; per rank, step and "
+                             "repetition: flk_set_objects(pinned host, 20 B/bird) + commit + Bird::step + exchange + "
+                             "lazy_update + flk_dist_snapshot_owned_async(pinned host, 20 B/bird); output feeds the next "
+                             "step's input; bytes are per rank; serial_value = one repetition alone"}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on the host cores, bounded sample ----
     cpu = None

@@ -67,6 +67,7 @@ SIGNATURES = {
     "flk_dist_num_owned": [_vp, _P(_u64)],
     "flk_dist_commit": [_vp],
     "flk_dist_snapshot_owned": [_vp, _vp, _vp, _vp, _P(_u64)],
+    "flk_dist_snapshot_owned_async": [_vp, _vp, _vp, _vp, _P(_u64)],
     "flk_mgpu_create": [_f32, _f32, _f32, _u64, C.c_int, _P(C.c_int), _P(_vp)],
     "flk_mgpu_commit": [_P(_vp), C.c_int],
     "flk_mgpu_step": [_P(_vp), C.c_int, _u64, _u64, _vp, _u64],

@@ -594,9 +594,9 @@ int flk_dist_num_owned(flk_field *f, uint64_t *n) {
 }
 
 // snapshot of the birds this rank OWNS (ghost copies excluded), (cell, id) order
-int flk_dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n) {
+static int dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n, bool sync) {
     CHECK_HANDLE(f);
-    if (f->g.mode != 1) return flk_snapshot(f, id, loc, last_d, n);
+    if (f->g.mode != 1) return sync ? flk_snapshot(f, id, loc, last_d, n) : flk_snapshot_async(f, id, loc, last_d, n);
     int rc = dist_check_errors(f);
     if (rc) return rc;
     uint32_t b[4];
@@ -625,8 +625,16 @@ int flk_dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_
         if (n0) CUDA_TRY(cudaMemcpyAsync(id, f->s.ids + b[0], n0 * 4, cudaMemcpyDeviceToHost, f->stream));
         if (n1) CUDA_TRY(cudaMemcpyAsync(id + n0, f->s.ids + b[2], n1 * 4, cudaMemcpyDeviceToHost, f->stream));
     }
-    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    if (sync) CUDA_TRY(cudaStreamSynchronize(f->stream));
     return FLK_OK;
+}
+
+int flk_dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n) {
+    return dist_snapshot_owned(f, id, loc, last_d, n, true);
+}
+
+int flk_dist_snapshot_owned_async(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n) {
+    return dist_snapshot_owned(f, id, loc, last_d, n, false);
 }
 
 }  // extern "C"

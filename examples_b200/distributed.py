@@ -74,6 +74,13 @@ class _StripField(Field2D):
         check(self._L.flk_dist_snapshot_owned(self._h, C.c_void_p(id_ptr), C.c_void_p(loc_ptr), C.c_void_p(ld_ptr), C.byref(n)))
         return n.value
 
+    def snapshot_owned_async_raw(self, id_ptr, loc_ptr, ld_ptr) -> int:
+        """count now, records after synchronize() (pinned buffers)"""
+        n = C.c_uint64()
+        check(self._L.flk_dist_snapshot_owned_async(self._h, C.c_void_p(id_ptr), C.c_void_p(loc_ptr), C.c_void_p(ld_ptr),
+                                                    C.byref(n)))
+        return n.value
+
     def snapshot_owned(self):
         cap = self.capacity
         ids = np.zeros(cap, dtype=np.uint32)

@@ -209,6 +209,10 @@ int flk_dist_num_owned(flk_field *f, uint64_t *n);
 /* flk_snapshot restricted to the birds this rank owns */
 int flk_dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n);
 
+/* as above, but the copies of the records are only enqueued: *n is exact on return (the call waits for the tick that
+ * produced the READ buffer), the HOST arrays (pinned) are valid after flk_synchronize */
+int flk_dist_snapshot_owned_async(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n);
+
 /* ---- multi-GPU, one host thread driving n strips (single process; peer copies instead of NCCL) -------- */
 /* out[n] receives one handle per strip; devices[r] is the CUDA ordinal of strip r (ordinals may repeat). */
 int flk_mgpu_create(float width, float height, float discretization, uint64_t capacity_per_rank, int n,

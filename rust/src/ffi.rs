@@ -66,6 +66,7 @@ extern "C" {
     pub fn flk_dist_step(f: *mut flk_field, step: u64, seed: u64, injected_r: *const c_float, n_injected: u64) -> c_int;
     pub fn flk_dist_num_owned(f: *mut flk_field, n: *mut u64) -> c_int;
     pub fn flk_dist_snapshot_owned(f: *mut flk_field, id: *mut u32, loc: *mut c_float, last_d: *mut c_float, n: *mut u64) -> c_int;
+    pub fn flk_dist_snapshot_owned_async(f: *mut flk_field, id: *mut u32, loc: *mut c_float, last_d: *mut c_float, n: *mut u64) -> c_int;
     pub fn flk_mgpu_create(width: c_float, height: c_float, discretization: c_float, capacity_per_rank: u64, n: c_int,
                            devices: *const c_int, out: *mut *mut flk_field) -> c_int;
     pub fn flk_mgpu_commit(handles: *mut *mut flk_field, n: c_int) -> c_int;
