@@ -17,6 +17,7 @@
 #include <dlfcn.h>
 
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 
 #include "../../include/flk.h"
@@ -96,6 +97,7 @@ struct flk_dist_state {
     bool have_known = false;
     bool overlap = true;               // FLK_DIST_OVERLAP=0 steps all columns before the exchange (A/B measurements)
     bool committed = false;
+    std::vector<int> bounds;           // world+1 global column boundaries: strip r owns [bounds[r], bounds[r+1])
 };
 
 namespace flk {
@@ -121,9 +123,24 @@ static void strip_of(int mx, int world, int rank, int *c0, int *c1) {
     *c1 = (int)((long long)(rank + 1) * mx / world);
 }
 
+// strip boundaries: the equal-width default or the caller's (Kdtree-style partition by population, flk_balance_columns)
+static int make_bounds(int mx, int world, const int32_t *col_bounds, std::vector<int> &b) {
+    b.resize(world + 1);
+    for (int r = 0; r <= world; ++r) {
+        int c0, c1;
+        if (col_bounds) b[r] = col_bounds[r];
+        else if (r == world) b[r] = mx;
+        else { strip_of(mx, world, r, &c0, &c1); b[r] = c0; }
+    }
+    if (b[0] != 0 || b[world] != mx) return fail(FLK_E_INVALID, "column boundaries must start at 0 and end at %d", mx);
+    for (int r = 0; r < world; ++r)
+        if (b[r + 1] - b[r] < 2) return fail(FLK_E_UNSUPPORTED, "strip %d would be %d columns wide (minimum 2)", r, b[r + 1] - b[r]);
+    return FLK_OK;
+}
+
 // common part of flk_dist_create / flk_mgpu_create
 static int dist_field_new(float w, float h, float disc, uint64_t capacity, int device, int rank, int world,
-                          int transport, flk_field **out) {
+                          int transport, flk_field **out, const int32_t *col_bounds = nullptr) {
     *out = nullptr;
     if (world < 2) return fail(FLK_E_INVALID, "strip decomposition needs world >= 2 (use flk_field_create for one GPU)");
     if (rank < 0 || rank >= world) return fail(FLK_E_INVALID, "rank %d out of range", rank);
@@ -142,8 +159,12 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
         delete f;
         return fail(FLK_E_UNSUPPORTED, "%d cell columns cannot be split into %d strips of >= 2 columns", g.mx, world);
     }
-    int c0, c1;
-    strip_of(g.mx, world, rank, &c0, &c1);
+    std::vector<int> bounds;
+    rc = make_bounds(g.mx, world, col_bounds, bounds);
+    if (rc) { delete f; return rc; }
+    const int c0 = bounds[rank], c1 = bounds[rank + 1];
+    int narrowest = g.mx;
+    for (int r = 0; r < world; ++r) narrowest = std::min(narrowest, bounds[r + 1] - bounds[r]);
     g.mode = 1; g.col0 = c0; g.nown = c1 - c0; g.has_slack = (c0 == 0);
     g.ncols = g.nown + 3;
     f->p = Params{0.8f, 1.0f, 1.1f, 0.7f, 1.0f, 0.7f, 10.0f, 1, 1};
@@ -152,8 +173,8 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     f->cap = capacity;
     f->ncell = (uint32_t)g.ncols * (uint32_t)g.dh;
     // exchange capacity: the two boundary columns hold ~2/nown of the strip; allow 8x that (clustered flocks).
-    // Must be identical on every rank (it fixes the message layout), hence the narrowest strip width mx/world.
-    uint64_t capx = 8 * (capacity / (uint64_t)(g.mx / world)) + 4096;
+    // Must be identical on every rank (it fixes the message layout), hence the narrowest strip width.
+    uint64_t capx = 8 * (capacity / (uint64_t)narrowest) + 4096;
     if (capx > capacity) capx = capacity;
     f->s.capx = (uint32_t)capx;
     CUDA_TRY(cudaSetDevice(device));
@@ -165,6 +186,7 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     flk_dist_state *d = new flk_dist_state();
     f->dist = d;
     d->rank = rank; d->world = world; d->transport = transport;
+    d->bounds = bounds;
     if (const char *e = getenv("FLK_DIST_OVERLAP")) d->overlap = atoi(e) != 0;
     d->left = (rank + world - 1) % world;
     d->right = (rank + 1) % world;
@@ -392,10 +414,15 @@ int flk_dist_unique_id(uint8_t *id128) {
 
 int flk_dist_create(float width, float height, float discretization, uint64_t capacity, int device, int rank, int world,
                     const uint8_t *id128, flk_field **out) {
+    return flk_dist_create_cols(width, height, discretization, capacity, device, rank, world, id128, nullptr, out);
+}
+
+int flk_dist_create_cols(float width, float height, float discretization, uint64_t capacity, int device, int rank,
+                         int world, const uint8_t *id128, const int32_t *col_bounds, flk_field **out) {
     if (!out || !id128) return fail(FLK_E_INVALID, "null argument");
     int rc = nccl_load();
     if (rc) return rc;
-    rc = dist_field_new(width, height, discretization, capacity, device, rank, world, 0, out);
+    rc = dist_field_new(width, height, discretization, capacity, device, rank, world, 0, out, col_bounds);
     if (rc) return rc;
     ncclUniqueId id;
     memcpy(id.internal, id128, 128);
@@ -411,10 +438,43 @@ int flk_dist_create(float width, float height, float discretization, uint64_t ca
 
 int flk_mgpu_create(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
                     const int *devices, flk_field **out) {
+    return flk_mgpu_create_cols(width, height, discretization, capacity_per_rank, n, devices, nullptr, out);
+}
+
+// Kdtree-style partition along x: equal-population strip boundaries from a sample of the x coordinates
+int flk_balance_columns(const float *x, uint64_t n, uint64_t stride, float width, float discretization, int world,
+                        int32_t *col_bounds) {
+    if (!col_bounds || (n && !x) || world < 1 || stride == 0) return fail(FLK_E_INVALID, "bad argument");
+    if (!(width > 0.0f) || !(discretization > 0.0f)) return fail(FLK_E_INVALID, "width, discretization must be > 0");
+    const int mx = (int)std::ceil(width / discretization);
+    if (mx < 2 * world) return fail(FLK_E_UNSUPPORTED, "%d cell columns cannot be split into %d strips of >= 2 columns", mx, world);
+    std::vector<uint64_t> hist(mx, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+        const float q = std::floor(x[i * stride] / discretization);   // f32, like the device binning
+        int c = (q != q) ? 0 : (q >= (float)mx ? 0 : (q < 0.0f ? 0 : (int)q));   // the slack column belongs to strip 0
+        hist[c] += 1;
+    }
+    // greedy quantile cut: boundary r sits where the running count reaches r/world of the sample, every strip keeps
+    // at least 2 columns and leaves at least 2 for each strip still to come
+    col_bounds[0] = 0;
+    uint64_t run = 0;
+    int c = 0;
+    for (int r = 1; r < world; ++r) {
+        const uint64_t target = (uint64_t)((double)n * r / world);
+        const int lo = col_bounds[r - 1] + 2, hi = mx - 2 * (world - r);
+        while (c < hi && (c < lo || run + hist[c] / 2 < target)) run += hist[c++];
+        col_bounds[r] = c;
+    }
+    col_bounds[world] = mx;
+    return FLK_OK;
+}
+
+int flk_mgpu_create_cols(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
+                         const int *devices, const int32_t *col_bounds, flk_field **out) {
     if (!out || !devices || n < 2) return fail(FLK_E_INVALID, "need n >= 2 devices");
     flk_field **grp = new flk_field *[n];
     for (int r = 0; r < n; ++r) {
-        int rc = dist_field_new(width, height, discretization, capacity_per_rank, devices[r], r, n, 1, &grp[r]);
+        int rc = dist_field_new(width, height, discretization, capacity_per_rank, devices[r], r, n, 1, &grp[r], col_bounds);
         if (rc) {
             for (int q = 0; q < r; ++q) { grp[q]->dist->group = nullptr; flk_field_destroy(grp[q]); }
             delete[] grp;
@@ -454,11 +514,9 @@ int flk_dist_owner(const flk_field *f, float x, float y, int32_t *rank) {
     if (gc < 0) gc = 0;
     if (gc >= f->g.mx) { *rank = 0; return FLK_OK; }   // the slack column belongs to the strip holding column 0
     const int world = f->dist->world;
-    for (int r = 0; r < world; ++r) {
-        int c0, c1;
-        strip_of(f->g.mx, world, r, &c0, &c1);
-        if (gc >= c0 && gc < c1) { *rank = r; return FLK_OK; }
-    }
+    const std::vector<int> &b = f->dist->bounds;
+    for (int r = 0; r < world; ++r)
+        if (gc >= b[r] && gc < b[r + 1]) { *rank = r; return FLK_OK; }
     return fail(FLK_E_INVALID, "no owner for column %d", gc);
 }
 

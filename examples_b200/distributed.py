@@ -34,6 +34,15 @@ def owner_of_column(mx: int, world: int, col: int) -> int:
     raise ValueError(col)
 
 
+def balanced_columns(x, width, world: int, discretization=DISCRETIZATION) -> np.ndarray:
+    """Kdtree-style partition along x (flockers_mpi/src/model/state.rs:33): world+1 column boundaries such that every
+    strip holds about the same number of the sampled birds (flk_balance_columns)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros(world + 1, dtype=np.int32)
+    check(_lib.load().flk_balance_columns(_vp(x), x.size, 1, width, discretization, world, _vp(out)))
+    return out
+
+
 def column_of(x, discretization=DISCRETIZATION) -> np.ndarray:
     """floor(x/d) in f32, like Field2D's discretisation."""
     q = np.floor(np.asarray(x, dtype=np.float32) / np.float32(discretization))
@@ -101,7 +110,8 @@ class _StripField(Field2D):
 class DistField2D(_StripField):
     """One strip of the torus on this process's GPU; collective calls must be made by every rank."""
 
-    def __init__(self, width, height, discretization=DISCRETIZATION, capacity=1 << 20, device=0, rank=0, world=1):
+    def __init__(self, width, height, discretization=DISCRETIZATION, capacity=1 << 20, device=0, rank=0, world=1,
+                 col_bounds=None):
         import torch
         import torch.distributed as dist
         self._L = _lib.load()
@@ -115,7 +125,9 @@ class DistField2D(_StripField):
             uid = uid.cuda(device)
         dist.broadcast(uid, src=0)
         raw = (C.c_uint8 * 128)(*uid.cpu().tolist())
-        check(self._L.flk_dist_create(width, height, discretization, capacity, device, rank, world, raw, C.byref(self._h)))
+        cb = None if col_bounds is None else np.ascontiguousarray(col_bounds, dtype=np.int32)
+        check(self._L.flk_dist_create_cols(width, height, discretization, capacity, device, rank, world, raw, _vp(cb),
+                                           C.byref(self._h)))
         self.width, self.height, self.discretization, self.toroidal = width, height, discretization, True
         self.capacity, self.rank, self.world = capacity, rank, world
         dw, dh, mx, my = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
@@ -140,13 +152,15 @@ class MgpuGroup:
     """n strips in one process.  `devices[r]` is the CUDA ordinal of strip r (ordinals may repeat: that is how
     the strip logic is exercised on a single GPU)."""
 
-    def __init__(self, width, height, discretization=DISCRETIZATION, capacity_per_rank=1 << 20, devices=(0, 0)):
+    def __init__(self, width, height, discretization=DISCRETIZATION, capacity_per_rank=1 << 20, devices=(0, 0),
+                 col_bounds=None):
         self._L = _lib.load()
         n = len(devices)
         self.n = n
         self._arr = (C.c_void_p * n)()
         devs = (C.c_int * n)(*devices)
-        check(self._L.flk_mgpu_create(width, height, discretization, capacity_per_rank, n, devs, self._arr))
+        cb = None if col_bounds is None else np.ascontiguousarray(col_bounds, dtype=np.int32)
+        check(self._L.flk_mgpu_create_cols(width, height, discretization, capacity_per_rank, n, devs, _vp(cb), self._arr))
         self.fields = []
         for r in range(n):
             f = _StripField._adopt(C.c_void_p(self._arr[r]), width, height, discretization, capacity_per_rank)
@@ -180,7 +194,7 @@ class MgpuGroup:
         last_d = np.asarray(last_d, dtype=np.float32).reshape(-1, 2)
         col = column_of(loc[:, 0], self.fields[0].discretization)
         for r, f in enumerate(self.fields):
-            c0, c1 = strip_of(self.mx, self.n, r)
+            c0, c1 = f.strip()
             m = (col >= c0) & (col < c1)
             if r == 0:
                 m |= col >= self.mx

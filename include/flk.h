@@ -189,6 +189,17 @@ int flk_dist_unique_id(uint8_t id128[128]);
 int flk_dist_create(float width, float height, float discretization, uint64_t capacity, int device,
                     int rank, int world, const uint8_t id128[128], flk_field **out);
 
+/* The same with explicit strip boundaries: col_bounds[world+1] global cell columns, col_bounds[0] = 0,
+ * col_bounds[world] = ceil(width/discretization), every strip at least 2 columns wide; identical on every rank.
+ * NULL = equal widths.  This is the Kdtree partition of flockers_mpi (state.rs:33) restricted to one axis. */
+int flk_dist_create_cols(float width, float height, float discretization, uint64_t capacity, int device,
+                         int rank, int world, const uint8_t id128[128], const int32_t *col_bounds, flk_field **out);
+
+/* Boundaries that give every strip about the same number of birds: x[i*stride] (HOST) is the x coordinate of sampled
+ * bird i (stride in floats: 1 for a plain array, 2 for interleaved loc, 4 for rec4).  Host-side, no device needed. */
+int flk_balance_columns(const float *x, uint64_t n, uint64_t stride, float width, float discretization, int world,
+                        int32_t *col_bounds);
+
 /* get_block_by_location (flockers_mpi/src/model/state.rs:75, bird.rs:190): owner rank of a location */
 int flk_dist_owner(const flk_field *f, float x, float y, int32_t *rank);
 /* global cell-column range [col0,col1) owned by this rank */
@@ -217,6 +228,8 @@ int flk_dist_snapshot_owned_async(flk_field *f, uint32_t *id, float *loc, float 
 /* out[n] receives one handle per strip; devices[r] is the CUDA ordinal of strip r (ordinals may repeat). */
 int flk_mgpu_create(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
                     const int *devices, flk_field **out);
+int flk_mgpu_create_cols(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
+                         const int *devices, const int32_t *col_bounds, flk_field **out);
 int flk_mgpu_commit(flk_field **handles, int n);
 int flk_mgpu_step(flk_field **handles, int n, uint64_t step, uint64_t seed, const float *injected_r,
                   uint64_t n_injected);

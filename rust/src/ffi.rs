@@ -60,6 +60,12 @@ extern "C" {
     pub fn flk_dist_unique_id(id128: *mut u8) -> c_int;
     pub fn flk_dist_create(width: c_float, height: c_float, discretization: c_float, capacity: u64, device: c_int,
                            rank: c_int, world: c_int, id128: *const u8, out: *mut *mut flk_field) -> c_int;
+    pub fn flk_dist_create_cols(width: c_float, height: c_float, discretization: c_float, capacity: u64, device: c_int,
+                                rank: c_int, world: c_int, id128: *const u8, col_bounds: *const i32, out: *mut *mut flk_field) -> c_int;
+    pub fn flk_balance_columns(x: *const c_float, n: u64, stride: u64, width: c_float, discretization: c_float, world: c_int,
+                               col_bounds: *mut i32) -> c_int;
+    pub fn flk_mgpu_create_cols(width: c_float, height: c_float, discretization: c_float, capacity_per_rank: u64, n: c_int,
+                                devices: *const c_int, col_bounds: *const i32, out: *mut *mut flk_field) -> c_int;
     pub fn flk_dist_owner(f: *const flk_field, x: c_float, y: c_float, rank: *mut i32) -> c_int;
     pub fn flk_dist_strip(f: *const flk_field, col0: *mut i32, col1: *mut i32) -> c_int;
     pub fn flk_dist_commit(f: *mut flk_field) -> c_int;

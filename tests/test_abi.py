@@ -78,3 +78,28 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in text.lower(), f"{fn} mentions the oracle"
+
+
+def test_balance_columns_is_host_side_and_balanced(lib):
+    """flk_balance_columns (the Kdtree-style partition along x) needs no device"""
+    import ctypes as C
+    import numpy as np
+    from examples_b200.distributed import balanced_columns, column_of, grid_columns
+    W = 1000.0
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.normal(200.0, 30.0, 30000), rng.uniform(0, W, 10000)]).astype(np.float32)
+    x = np.mod(x, np.float32(W)).astype(np.float32)
+    mx = grid_columns(W)
+    for world in (1, 2, 3, 8):
+        b = balanced_columns(x, W, world)
+        assert b[0] == 0 and b[-1] == mx and np.all(np.diff(b) >= 2)
+        col = column_of(x)
+        counts = np.array([np.sum((col >= b[r]) & (col < b[r + 1])) for r in range(world)])
+        assert counts.sum() == x.size
+        if world > 1:
+            assert counts.max() < 2.2 * x.size / world, (world, counts)     # equal widths would put ~80 % in one strip
+    # a uniform sample gives (nearly) equal widths; too many strips for the grid is an error
+    u = rng.uniform(0, W, 50000).astype(np.float32)
+    assert np.abs(np.diff(balanced_columns(u, W, 5)) - mx / 5).max() <= 3
+    out = (C.c_int32 * 200)()
+    assert lib.load().flk_balance_columns(u.ctypes.data_as(C.c_void_p), u.size, 1, W, 6.6666665, 100, out) < 0

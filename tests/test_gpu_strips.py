@@ -143,3 +143,43 @@ def test_capacity_overflow_after_exchange_is_reported():
     with pytest.raises(FlkError) as e:
         g.num_owned()
     assert e.value.code == -3
+
+
+def test_population_balanced_strips_match_single_field():
+    """Kdtree-style boundaries (flk_balance_columns): clustered flocks, uneven strip widths, same result bit for bit"""
+    from examples_b200.distributed import MgpuGroup, balanced_columns, grid_columns
+    W, H = 600.0, 300.0
+    n = 12000
+    birds = clustered_birds(n, W, H, per_cluster=1500, sigma=12.0)
+    birds["x"] = (birds["x"] * np.float32(0.5)).astype(np.float32)       # everything in the left half of the field
+    ids, loc, ld = to_arrays(birds)
+    bounds = balanced_columns(loc[:, 0], W, 4)
+    mx = grid_columns(W)
+    assert bounds[0] == 0 and bounds[-1] == mx and np.all(np.diff(bounds) >= 2)
+    assert bounds[3] <= mx // 2 + 2                                      # three of the four strips inside the left half
+    f = single(birds, W, H)
+    g = MgpuGroup(W, H, D, capacity_per_rank=n, devices=[0] * 4, col_bounds=bounds)
+    assert [fld.strip() for fld in g.fields] == [(int(bounds[r]), int(bounds[r + 1])) for r in range(4)]
+    g.scatter_objects(ids, loc, ld)
+    g.commit()
+    owned0 = g.num_owned()
+    assert sum(owned0) == n and max(owned0) < 0.45 * n                   # equal widths would give strip 0 about half
+    for t0 in range(0, 40, 10):
+        f.run(t0, 10)
+        g.run(t0, 10)
+        assert bits_equal(from_arrays(*g.snapshot_by_id()), from_arrays(*f.snapshot_by_id())), t0
+    for r, fld in enumerate(g.fields):                                   # get_block_by_location follows the boundaries
+        c0, c1 = fld.strip()
+        assert fld.owner((c0 + 0.5) * D, 1.0) == r and fld.owner((c1 - 0.5) * D, 1.0) == r
+    assert g.fields[2].owner(W, 0.0) == 0                                # the slack column belongs to strip 0
+    g.close()
+
+
+def test_bad_strip_boundaries_are_rejected():
+    from examples_b200 import _lib
+    from examples_b200.distributed import MgpuGroup, grid_columns
+    W = 200.0
+    mx = grid_columns(W)
+    for bad in ([0, 1, mx], [0, mx // 2, mx - 1], [1, mx // 2, mx], [0, mx, mx]):
+        with pytest.raises(_lib.FlkError):
+            MgpuGroup(W, W, D, capacity_per_rank=100, devices=[0, 0], col_bounds=bad)
