@@ -315,7 +315,7 @@ __device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, cons
 
 // interior accumulation out of the CTA's shared-memory tile (same order, same arithmetic as accumulate_interior)
 #ifndef FLK_SMEM_UNROLL
-#define FLK_SMEM_UNROLL 1   // measured with the packed loop: unroll 1 0.877 ms, 2 0.909 ms, 4 0.912 ms (no odd-length remainder pass)
+#define FLK_SMEM_UNROLL 2   // packed loop, k_step ms: without prefetch 1: 0.877, 2: 0.909, 4: 0.912; with prefetch 1: 0.901, 2: 0.856, 3: 0.892, 4: 0.896
 #endif
 constexpr int kSmemUnroll = FLK_SMEM_UNROLL;
 // SELF: the run contains the bird itself at index `self` (bird.rs:53 skips it by id).  Its own record contributes
@@ -342,6 +342,9 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 #ifndef FLK_PACKMASK
 #define FLK_PACKMASK 7
 #endif
+#ifndef FLK_PREFETCH
+#define FLK_PREFETCH 1   // next candidate's LDS.128 issued before the current one is consumed (with unroll 2: 0.867 -> 0.856 ms)
+#endif
 template <bool SELF>
 __device__ __forceinline__ void accumulate_run_smem_packed(const float4 *tile, uint32_t j, uint32_t e, uint32_t self,
                                                            f32x2 ME, f32x2 &A, f32x2 &Cc, f32x2 &Ss) {
@@ -349,9 +352,17 @@ __device__ __forceinline__ void accumulate_run_smem_packed(const float4 *tile, u
     const f32x2 NEG1 = pk(-1.0f, -1.0f);
     float mx_, my_;
     unpk(ME, mx_, my_);
+#if FLK_PREFETCH
+    ulonglong2 nxt = t2[j];   // one slot past a run is still inside the tile array (padded by one record)
+#endif
 #pragma unroll kSmemUnroll
     for (; j < e; ++j) {
+#if FLK_PREFETCH
+        ulonglong2 o = nxt;
+        nxt = t2[j + 1];
+#else
         ulonglong2 o = t2[j];
+#endif
         if (SELF && j == self) o.y = 0ull;                     // (last_d) := (+0,+0), see accumulate_run_smem
         f32x2 Dv;
         float dx, dy, s0, s1;
@@ -454,13 +465,14 @@ __device__ __noinline__ void step_bird_general(const Geom &g, const Params &p, c
 // FASTG = the host checked what does not depend on the bird (launch_step): toroidal field, 3x3 window, relax query,
 // grid >= 6x6 cells, discretisation in the shared-reciprocal range, no payload, not the identity pass.
 #ifndef FLK_STEP_MINBLOCKS
-#define FLK_STEP_MINBLOCKS 10   // 48 registers; measured 0.858-0.867 ms against 0.872-0.876 (12), 0.885 (13-16), 0.925 (8)
+#define FLK_STEP_MINBLOCKS 9   // 56 registers; with the prefetching loop: 0.851 ms (9), 0.856 (10), 0.884 (12)
 #endif
 template <bool RELAX, int MATH, bool TILE, bool FASTG>
 __global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS)
 k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const __grid_constant__ Store s,
        const __grid_constant__ StepArgs a) {
-    __shared__ __align__(128) float4 tile[TILE ? 3 : 1][TILE ? TILE_CAP : 1];
+    __shared__ __align__(128) float4 tile_s[TILE ? 3 * TILE_CAP + 1 : 1];
+    float4 *const tile[3] = {tile_s, tile_s + (TILE ? TILE_CAP : 0), tile_s + (TILE ? 2 * TILE_CAP : 0)};
     __shared__ __align__(8) uint64_t bar;
     __shared__ int shc[5];
 
