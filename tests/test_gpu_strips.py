@@ -183,3 +183,35 @@ def test_bad_strip_boundaries_are_rejected():
     for bad in ([0, 1, mx], [0, mx // 2, mx - 1], [1, mx // 2, mx], [0, mx, mx]):
         with pytest.raises(_lib.FlkError):
             MgpuGroup(W, W, D, capacity_per_rank=100, devices=[0, 0], col_bounds=bad)
+
+
+def test_async_owned_snapshot_equals_the_synchronous_one():
+    """flk_dist_snapshot_owned_async: exact count on return, records valid after synchronize (pinned buffers)"""
+    import ctypes as C
+    from examples_b200 import _lib
+    L = _lib.load()
+    W = 300.0
+    n = 5000
+    birds = uniform_birds(n, W, W)
+    g = group(birds, W, W, 3)
+    g.run(0, 7)
+    for f in g.fields:
+        ids, loc, ld = f.snapshot_owned()
+        k = len(ids)
+        ptrs = []
+        for nbytes in (4 * n, 8 * n, 8 * n):
+            p = C.c_void_p()
+            _lib.check(L.flk_host_alloc(C.byref(p), nbytes))
+            ptrs.append(p)
+        try:
+            got = f.snapshot_owned_async_raw(ptrs[0].value, ptrs[1].value, ptrs[2].value)
+            assert got == k
+            f.synchronize()
+            a_id = np.ctypeslib.as_array(C.cast(ptrs[0], C.POINTER(C.c_uint32)), shape=(n,))[:k]
+            a_loc = np.ctypeslib.as_array(C.cast(ptrs[1], C.POINTER(C.c_float)), shape=(n, 2))[:k]
+            a_ld = np.ctypeslib.as_array(C.cast(ptrs[2], C.POINTER(C.c_float)), shape=(n, 2))[:k]
+            assert np.array_equal(a_id, ids) and bits_equal(np.array(a_loc), loc) and bits_equal(np.array(a_ld), ld)
+        finally:
+            for p in ptrs:
+                L.flk_host_free(p)
+    g.close()
