@@ -237,8 +237,8 @@ def run_ours(args, world: int, rank: int, local_rank: int):
         id_base = 0
     else:
         from examples_b200 import distributed as fdist
-        f = fdist.DistField2D(W, H, D, capacity=cap, device=local_rank, rank=rank, world=world)
-        c0, c1 = f.strip()
+        f = fdist.DistField2D(W, H, D, capacity=cap, device=local_rank, rank=rank, world=world, tile_rows=args.tile_rows)
+        c0, c1, r0, r1 = f.tile()
         x0 = float(np.float32(c0) * np.float32(D))
         x1 = float(np.float32(c1) * np.float32(D)) if c1 < gx else W
         loc = make_birds(n_local, W, H, clustered, x0, x1, seed=INIT_SEED + rank)
@@ -246,6 +246,13 @@ def run_ours(args, world: int, rank: int, local_rank: int):
         col = fdist.column_of(loc[:, 0], D)
         off = (col < c0) | (col >= c1)
         loc[off, 0] = np.float32(0.5 * (x0 + x1))
+        if args.tile_rows > 1:   # tiles: squeeze the y coordinates into the rows this rank owns
+            y0 = float(np.float32(r0) * np.float32(D))
+            y1 = float(np.float32(r1) * np.float32(D)) if r1 < gy else H
+            loc[:, 1] = (np.float32(y0) + np.float32(y1 - y0) * (loc[:, 1] / np.float32(H))).astype(np.float32)
+            row = fdist.column_of(loc[:, 1], D)
+            off = (row < r0) | (row >= r1)
+            loc[off, 1] = np.float32(0.5 * (y0 + y1))
         id_base = rank * n_local
     # pinned host buffers: the host-side copy of the agents (what krABMaga's Schedule holds)
     h_id = torch.arange(id_base, id_base + n_local, dtype=torch.int64).to(torch.uint32).pin_memory() \
@@ -392,7 +399,8 @@ def run_ours(args, world: int, rank: int, local_rank: int):
             assert int(total) == R * n_total, (total, R * n_total)
             return R * n_total * steps / dt
 
-        extra = [fdist.DistField2D(W, H, D, capacity=cap, device=local_rank, rank=rank, world=world) for _ in range(reps - 1)]
+        extra = [fdist.DistField2D(W, H, D, capacity=cap, device=local_rank, rank=rank, world=world, tile_rows=args.tile_rows)
+                 for _ in range(reps - 1)]
         for fx in extra:
             fx.set_math_mode(args.math)
         serial_value = e2e_run_dist([f], e2e_steps)
@@ -419,7 +427,9 @@ def run_ours(args, world: int, rank: int, local_rank: int):
             "higher_is_better": True, "scaling": "strong" if args.workload == "strong16m" else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": label, "birds_total": n_total, "birds_per_gpu": n_total // world,
-                       "decomposition": "single GPU" if world == 1 else f"x-strips over {world} GPUs, NCCL halo+migration",
+                       "decomposition": "single GPU" if world == 1 else
+                                        (f"x-strips over {world} GPUs, NCCL halo+migration" if args.tile_rows == 1 else
+                                         f"{world // args.tile_rows} x {args.tile_rows} tiles over {world} GPUs, NCCL halo+migration in two hops"),
                        "math": "exact (IEEE f32, bit-identical to the oracle)" if args.math == 0 else "fast",
                        "l2": "inputs larger than L2 (>=20 B/bird x birds per GPU vs 126 MB)" if n_total // world >= 8_000_000
                              else "working set fits L2 (reference config size)",
@@ -451,6 +461,7 @@ def main():
     ap.add_argument("--workload", default="weak16m", choices=["weak16m", "strong16m", "1m", "clustered"])
     ap.add_argument("--birds-per-gpu", type=int, default=None)
     ap.add_argument("--math", type=int, default=0)
+    ap.add_argument("--tile-rows", type=int, default=1)   # > 1: split the rows too (tiles); default = x-strips
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-reps", type=int, default=3)           # independent repetitions pipelined in the e2e leg
     ap.add_argument("--cpu-birds", type=int, default=1_000_000)   # birds of the CPU sample (per tick)

@@ -71,6 +71,9 @@ SIGNATURES = {
     "flk_dist_snapshot_owned_async": [_vp, _vp, _vp, _vp, _P(_u64)],
     "flk_mgpu_create": [_f32, _f32, _f32, _u64, C.c_int, _P(C.c_int), _P(_vp)],
     "flk_mgpu_create_cols": [_f32, _f32, _f32, _u64, C.c_int, _P(C.c_int), _vp, _P(_vp)],
+    "flk_dist_create_tiles": [_f32, _f32, _f32, _u64, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _P(_vp)],
+    "flk_mgpu_create_tiles": [_f32, _f32, _f32, _u64, C.c_int, _P(C.c_int), C.c_int, _vp, _vp, _P(_vp)],
+    "flk_dist_tile": [_vp, _P(_i32), _P(_i32), _P(_i32), _P(_i32)],
     "flk_balance_columns": [_vp, _u64, _u64, _f32, _f32, C.c_int, _vp],
     "flk_mgpu_commit": [_P(_vp), C.c_int],
     "flk_mgpu_step": [_P(_vp), C.c_int, _u64, _u64, _vp, _u64],

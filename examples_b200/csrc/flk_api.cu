@@ -31,8 +31,9 @@ int field_alloc(flk_field *f) {
     const uint64_t m = (uint64_t)f->ncell + 1;
     Store &s = f->s;
     s.cap = (uint32_t)cap;
-    if (f->g.mode != 1) s.capx = 0;
-    const uint64_t capw = cap + 2ull * s.capx;   // WRITE slots: stepped/uploaded + received from both neighbours
+    if (f->g.mode == 0) s.capx = 0;
+    s.nrecv = f->g.mode == 2 ? 4u : 2u;
+    const uint64_t capw = cap + (uint64_t)s.nrecv * s.capx;   // WRITE slots: stepped/uploaded + received from the neighbours
     CUDA_TRY(cudaMalloc(&s.rec, cap * sizeof(Rec)));
     CUDA_TRY(cudaMalloc(&s.ids, cap * 4));
     const uint64_t mp = ((m + 2047) / 2048) * 2048;   // padded to the scan tile (k_scan_* use whole-tile vector accesses)
@@ -88,6 +89,7 @@ int setup_geometry(flk_field *f, float w, float h, float d, int toroidal) {
     if (cw > 46000.0f || ch > 46000.0f) return fail(FLK_E_UNSUPPORTED, "grid too large (%g x %g cells)", cw, ch);
     g.mx = (int)cw; g.my = (int)ch;
     g.dh = g.my + 1;
+    g.dhg = g.dh; g.row0 = 0; g.rown = g.my; g.has_slack_row = 1;
     g.ncols = g.mx + 1;
     g.mode = 0; g.col0 = 0; g.nown = g.mx; g.has_slack = 1;
     return FLK_OK;
@@ -100,8 +102,8 @@ int update_window(flk_field *f) {
     if (f->p.radius > 0.0f && (2 * k + 1 > f->g.mx || 2 * k + 1 > f->g.my) && f->g.toroidal)
         return fail(FLK_E_UNSUPPORTED, "query window (%d cells) wider than the grid (%d x %d): duplicate visits are not implemented",
                     2 * k + 1, f->g.mx, f->g.my);
-    if (f->g.mode == 1 && k > 1) return fail(FLK_E_UNSUPPORTED, "strip decomposition implements a one-column halo (k<=1), got k=%d", k);
-    if (f->g.mode == 1 && !(std::fabs(f->p.jump) < f->g.d))
+    if (f->g.mode != 0 && k > 1) return fail(FLK_E_UNSUPPORTED, "strip decomposition implements a one-column halo (k<=1), got k=%d", k);
+    if (f->g.mode != 0 && !(std::fabs(f->p.jump) < f->g.d))
         return fail(FLK_E_UNSUPPORTED, "strip decomposition needs |jump| < discretisation (a bird may cross one column per tick)");
     f->p.k = k;
     return FLK_OK;
@@ -113,7 +115,7 @@ int flush_pending(flk_field *f) {
     std::vector<uint32_t> id;
     std::vector<float> loc, ld;
     id.swap(f->pend_id); loc.swap(f->pend_loc); ld.swap(f->pend_ld);
-    if (f->g.mode == 1) return dist_set_objects(f, id.size(), id.data(), loc.data(), ld.data());
+    if (f->g.mode != 0) return dist_set_objects(f, id.size(), id.data(), loc.data(), ld.data());
     return write_append(f, id.size(), id.data(), loc.data(), ld.data());
 }
 
@@ -162,11 +164,11 @@ int enqueue_lazy_update(flk_field *f, int bump_step) {
     if (int rc = mark()) return rc;
     launch_scan(f->s, m, f->stream);
     if (int rc = mark()) return rc;
-    launch_scatter(f->s, (uint32_t)f->w_count, f->g.mode == 1, f->stream);
+    launch_scatter(f->s, (uint32_t)f->w_count, f->g.mode != 0, f->stream);
     if (int rc = mark()) return rc;
     launch_rank(f->s, (uint32_t)f->w_count, f->ncell, bump_step, f->stream);
     if (int rc = mark()) return rc;
-    f->launches += 3 + (f->g.mode == 1 ? 2 : (f->w_count ? 1 : 0)) + 1;
+    f->launches += 3 + (f->g.mode != 0 ? 2 : (f->w_count ? 1 : 0)) + 1;
     CUDA_TRY(cudaGetLastError());
     f->n_read = f->w_count;  // single GPU: every WRITE entry is kept
     f->w_count = 0;
@@ -310,7 +312,7 @@ int flk_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *l
     if (n && (!id || !loc || !last_d)) return fail(FLK_E_INVALID, "null array");
     int rc = flush_pending(f);
     if (rc) return rc;
-    if (f->g.mode == 1) return dist_set_objects(f, n, id, loc, last_d);
+    if (f->g.mode != 0) return dist_set_objects(f, n, id, loc, last_d);
     return write_append(f, n, id, loc, last_d);
 }
 
@@ -318,7 +320,7 @@ int flk_set_objects_ex(flk_field *f, uint64_t n, const uint32_t *id, const float
                        const void *payload) {
     CHECK_HANDLE(f);
     if (n && (!id || !loc || !last_d)) return fail(FLK_E_INVALID, "null array");
-    if (f->g.mode == 1) return fail(FLK_E_UNSUPPORTED, "payloads are not carried by strip handles");
+    if (f->g.mode != 0) return fail(FLK_E_UNSUPPORTED, "payloads are not carried by strip handles");
     int rc = flush_pending(f);
     if (rc) return rc;
     return write_append(f, n, id, loc, last_d, static_cast<const uint32_t *>(payload));
@@ -335,7 +337,7 @@ int flk_lazy_update(flk_field *f) {
     CHECK_HANDLE(f);
     int rc = flush_pending(f);
     if (rc) return rc;
-    if (f->g.mode == 1) return fail(FLK_E_STATE, "dist handles fold lazy_update into flk_dist_step / flk_dist_commit");
+    if (f->g.mode != 0) return fail(FLK_E_STATE, "dist handles fold lazy_update into flk_dist_step / flk_dist_commit");
     CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
     rc = enqueue_lazy_update(f, 0);
     if (rc) return rc;
@@ -347,7 +349,7 @@ int flk_step(flk_field *f, uint64_t step, uint64_t seed, const float *injected_r
     CHECK_HANDLE(f);
     int rc = flush_pending(f);
     if (rc) return rc;
-    if (f->g.mode == 1) return fail(FLK_E_STATE, "use flk_dist_step on a dist handle");
+    if (f->g.mode != 0) return fail(FLK_E_STATE, "use flk_dist_step on a dist handle");
     const float2 *d_inj = nullptr;
     if (injected_r) {
         rc = upload_injected(f, injected_r, n_injected);
@@ -365,7 +367,7 @@ int flk_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed) 
     CHECK_HANDLE(f);
     int rc = flush_pending(f);
     if (rc) return rc;
-    if (f->g.mode == 1) return dist_run(f, first_step, n_steps, seed);
+    if (f->g.mode != 0) return dist_run(f, first_step, n_steps, seed);
     if (f->w_count != 0) return fail(FLK_E_STATE, "flk_run needs an empty WRITE buffer (call flk_lazy_update first)");
     CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
     // a captured tick pays off from a handful of replays on; short runs without a cached graph launch directly
@@ -412,7 +414,7 @@ int flk_num_objects(const flk_field *f, uint64_t *n) {
 
 static int snapshot_impl(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n, bool sync) {
     CHECK_HANDLE(f);
-    if (f->g.mode == 1) { int rc = dist_refresh_counts(f); if (rc) return rc; }
+    if (f->g.mode != 0) { int rc = dist_refresh_counts(f); if (rc) return rc; }
     const uint64_t nr = f->n_read;
     if (n) *n = nr;
     if (nr) {
@@ -447,7 +449,7 @@ static uint32_t *dense_counter(flk_field *f) {
 int flk_set_objects_dense(flk_field *f, uint64_t n, uint32_t id0, const float *rec4) {
     CHECK_HANDLE(f);
     if (n && !rec4) return fail(FLK_E_INVALID, "null array");
-    if (f->g.mode == 1) return fail(FLK_E_UNSUPPORTED, "dense upload is for single-GPU handles (a strip owns arbitrary ids)");
+    if (f->g.mode != 0) return fail(FLK_E_UNSUPPORTED, "dense upload is for single-GPU handles (a strip owns arbitrary ids)");
     if ((uint64_t)id0 + n > 0x100000000ull) return fail(FLK_E_INVALID, "id range exceeds u32");
     int rc = flush_pending(f);
     if (rc) return rc;
@@ -467,7 +469,7 @@ int flk_set_objects_dense(flk_field *f, uint64_t n, uint32_t id0, const float *r
 static int snapshot_dense_impl(flk_field *f, uint32_t id0, uint64_t n, float *rec4, bool sync) {
     CHECK_HANDLE(f);
     if (n && !rec4) return fail(FLK_E_INVALID, "null array");
-    if (f->g.mode == 1) return fail(FLK_E_UNSUPPORTED, "dense snapshot is for single-GPU handles (a strip owns arbitrary ids)");
+    if (f->g.mode != 0) return fail(FLK_E_UNSUPPORTED, "dense snapshot is for single-GPU handles (a strip owns arbitrary ids)");
     if (n > f->cap) return fail(FLK_E_CAPACITY, "id range %llu larger than the capacity %llu", (unsigned long long)n, (unsigned long long)f->cap);
     if ((uint64_t)id0 + n > 0x100000000ull) return fail(FLK_E_INVALID, "id range exceeds u32");
     if (n == 0) return FLK_OK;
@@ -516,7 +518,7 @@ int flk_get_object(flk_field *f, uint32_t id, float out[4], int32_t *found) {
 
 int flk_get_binning(flk_field *f, uint32_t *cell_start, uint32_t *sorted_ids) {
     CHECK_HANDLE(f);
-    if (f->g.mode == 1) { int rc = dist_refresh_counts(f); if (rc) return rc; }
+    if (f->g.mode != 0) { int rc = dist_refresh_counts(f); if (rc) return rc; }
     if (cell_start)
         CUDA_TRY(cudaMemcpyAsync(cell_start, f->s.cell_start, ((uint64_t)f->ncell + 1) * 4, cudaMemcpyDeviceToHost, f->stream));
     if (sorted_ids && f->n_read)
@@ -536,7 +538,7 @@ int flk_query_batch(flk_field *f, uint64_t nq, const float *loc, float dist, int
         const int k = (int)std::floor(dist / f->g.d);
         if (f->g.toroidal && (2 * k + 1 > f->g.mx || 2 * k + 1 > f->g.my))
             return fail(FLK_E_UNSUPPORTED, "query window wider than the grid");
-        if (f->g.mode == 1 && k > 1) return fail(FLK_E_UNSUPPORTED, "dist handles answer queries with k<=1 only");
+        if (f->g.mode != 0 && k > 1) return fail(FLK_E_UNSUPPORTED, "dist handles answer queries with k<=1 only");
     }
     float2 *d_loc = nullptr;
     uint32_t *d_counts = nullptr, *d_out = nullptr;

@@ -97,7 +97,13 @@ struct flk_dist_state {
     bool have_known = false;
     bool overlap = true;               // FLK_DIST_OVERLAP=0 steps all columns before the exchange (A/B measurements)
     bool committed = false;
-    std::vector<int> bounds;           // world+1 global column boundaries: strip r owns [bounds[r], bounds[r+1])
+    std::vector<int> bounds;           // column boundaries: strip / tile column px owns [bounds[px], bounds[px+1])
+    // tiles (mode 2): ranks form a Px x Py grid, rank = py*Px + px; rows are split like the columns
+    int Px = 1, Py = 1, px = 0, py = 0;
+    int down = 0, up = 0;
+    std::vector<int> rbounds;          // row boundaries (Py+1)
+    cudaEvent_t ev_fwd = nullptr;      // my lower/upper messages are complete (own successors + forwarded arrivals)
+    cudaEvent_t ev_copied_y = nullptr; // the row-direction exchange is complete
 };
 
 namespace flk {
@@ -113,6 +119,8 @@ void dist_free(flk_field *f) {
     if (d->ev_sent) cudaEventDestroy(d->ev_sent);
     if (d->ev_tick) cudaEventDestroy(d->ev_tick);
     if (d->ev_copied) cudaEventDestroy(d->ev_copied);
+    if (d->ev_fwd) cudaEventDestroy(d->ev_fwd);
+    if (d->ev_copied_y) cudaEventDestroy(d->ev_copied_y);
     if (d->rank == 0 && d->group) delete[] d->group;
     delete d;
     f->dist = nullptr;
@@ -140,7 +148,8 @@ static int make_bounds(int mx, int world, const int32_t *col_bounds, std::vector
 
 // common part of flk_dist_create / flk_mgpu_create
 static int dist_field_new(float w, float h, float disc, uint64_t capacity, int device, int rank, int world,
-                          int transport, flk_field **out, const int32_t *col_bounds = nullptr) {
+                          int transport, flk_field **out, const int32_t *col_bounds = nullptr, int Py = 1,
+                          const int32_t *row_bounds = nullptr) {
     *out = nullptr;
     if (world < 2) return fail(FLK_E_INVALID, "strip decomposition needs world >= 2 (use flk_field_create for one GPU)");
     if (rank < 0 || rank >= world) return fail(FLK_E_INVALID, "rank %d out of range", rank);
@@ -155,18 +164,27 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     int rc = setup_geometry(f, w, h, disc, 1);
     if (rc) { delete f; return rc; }
     Geom &g = f->g;
-    if (g.mx < 2 * world) {
+    if (Py < 1 || world % Py != 0) { delete f; return fail(FLK_E_INVALID, "%d ranks do not form a grid with %d rows", world, Py); }
+    const int Px = world / Py, px = rank % Px, py = rank / Px;
+    if (Py > 1 && Px < 2) { delete f; return fail(FLK_E_UNSUPPORTED, "a tile grid needs at least 2 x 2 ranks (use strips for one row or column)"); }
+    if (g.mx < 2 * Px || (Py > 1 && g.my < 2 * Py)) {
         delete f;
-        return fail(FLK_E_UNSUPPORTED, "%d cell columns cannot be split into %d strips of >= 2 columns", g.mx, world);
+        return fail(FLK_E_UNSUPPORTED, "%d x %d cells cannot be split into %d x %d tiles of >= 2 x 2 cells", g.mx, g.my, Px, Py);
     }
-    std::vector<int> bounds;
-    rc = make_bounds(g.mx, world, col_bounds, bounds);
+    std::vector<int> bounds, rbounds;
+    rc = make_bounds(g.mx, Px, col_bounds, bounds);
+    if (!rc && Py > 1) rc = make_bounds(g.my, Py, row_bounds, rbounds);
     if (rc) { delete f; return rc; }
-    const int c0 = bounds[rank], c1 = bounds[rank + 1];
+    const int c0 = bounds[px], c1 = bounds[px + 1];
     int narrowest = g.mx;
-    for (int r = 0; r < world; ++r) narrowest = std::min(narrowest, bounds[r + 1] - bounds[r]);
-    g.mode = 1; g.col0 = c0; g.nown = c1 - c0; g.has_slack = (c0 == 0);
+    for (int r = 0; r < Px; ++r) narrowest = std::min(narrowest, bounds[r + 1] - bounds[r]);
+    for (int r = 0; r < Py && Py > 1; ++r) narrowest = std::min(narrowest, rbounds[r + 1] - rbounds[r]);
+    g.mode = Py > 1 ? 2 : 1; g.col0 = c0; g.nown = c1 - c0; g.has_slack = (c0 == 0);
     g.ncols = g.nown + 3;
+    if (Py > 1) {   // rows laid out like the columns: lower ghost, owned, upper ghost, slack
+        g.row0 = rbounds[py]; g.rown = rbounds[py + 1] - rbounds[py]; g.has_slack_row = (g.row0 == 0);
+        g.dh = g.rown + 3;
+    }
     f->p = Params{0.8f, 1.0f, 1.1f, 0.7f, 1.0f, 0.7f, 10.0f, 1, 1};
     rc = update_window(f);
     if (rc) { delete f; return rc; }
@@ -186,13 +204,19 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     flk_dist_state *d = new flk_dist_state();
     f->dist = d;
     d->rank = rank; d->world = world; d->transport = transport;
-    d->bounds = bounds;
+    d->bounds = bounds; d->rbounds = rbounds;
+    d->Px = Px; d->Py = Py; d->px = px; d->py = py;
     if (const char *e = getenv("FLK_DIST_OVERLAP")) d->overlap = atoi(e) != 0;
-    d->left = (rank + world - 1) % world;
-    d->right = (rank + 1) % world;
+    d->left = py * Px + (px + Px - 1) % Px;
+    d->right = py * Px + (px + 1) % Px;
+    d->down = ((py + Py - 1) % Py) * Px + px;
+    d->up = ((py + 1) % Py) * Px + px;
     const size_t xb = (xbuf_bytes(f->s.capx) + 255) & ~(size_t)255;
-    cudaError_t e = cudaMalloc(&d->xbuf, 4 * xb);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d->xbuf, 0, 4 * xb, f->stream);
+    const int nbuf = Py > 1 ? 8 : 4;
+    cudaError_t e = cudaMalloc(&d->xbuf, nbuf * xb);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d->xbuf, 0, nbuf * xb, f->stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fwd, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_copied_y, cudaEventDisableTiming);
     if (e == cudaSuccess) {
         int lo_p = 0, hi_p = 0;
         cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
@@ -208,6 +232,9 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
         return fail(FLK_E_CUDA, "dist alloc: %s", cudaGetErrorString(e));
     }
     f->s.sendL = d->xbuf; f->s.sendR = d->xbuf + xb; f->s.recvL = d->xbuf + 2 * xb; f->s.recvR = d->xbuf + 3 * xb;
+    if (Py > 1) {
+        f->s.sendD = d->xbuf + 4 * xb; f->s.sendU = d->xbuf + 5 * xb; f->s.recvD = d->xbuf + 6 * xb; f->s.recvU = d->xbuf + 7 * xb;
+    }
     f->n_read = 0;
     *out = f;
     return FLK_OK;
@@ -224,7 +251,7 @@ static uint32_t read_upper_bound(flk_field *f) {
         d->count_pending = false;
     }
     if (!d->have_known) return (uint32_t)f->cap;
-    const uint64_t b = d->known + (d->tick_no - d->known_tick) * 2ull * f->s.capx;
+    const uint64_t b = d->known + (d->tick_no - d->known_tick) * (uint64_t)f->s.nrecv * f->s.capx;
     return (uint32_t)(b < f->cap ? b : f->cap);
 }
 
@@ -237,6 +264,10 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
     flk_dist_state *d = f->dist;
     CUDA_TRY(cudaMemsetAsync(f->s.sendL, 0, sizeof(XHdr), f->stream));
     CUDA_TRY(cudaMemsetAsync(f->s.sendR, 0, sizeof(XHdr), f->stream));
+    if (f->g.mode == 2) {
+        CUDA_TRY(cudaMemsetAsync(f->s.sendD, 0, sizeof(XHdr), f->stream));
+        CUDA_TRY(cudaMemsetAsync(f->s.sendU, 0, sizeof(XHdr), f->stream));
+    }
     StepArgs a;
     a.step = step; a.use_step_dev = 0; a.seed = seed;
     a.injected = d_inj; a.n_injected = n_inj;
@@ -251,7 +282,7 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
         CUDA_TRY(cudaEventRecord(e0, f->stream));
     }
     const uint32_t dh = (uint32_t)f->g.dh, nown = (uint32_t)f->g.nown;
-    const bool split = nown >= 5 && d->overlap;
+    const bool split = nown >= 5 && d->overlap && f->g.mode == 1;   // tiles: border cells are not index ranges; no overlap yet
     if (split) {
         // border: columns {ghost, 1, 2} and {nown-1, nown, ghost, slack} (ghost threads only invalidate their WRITE
         // slot), on the high-priority comm stream so that they run BESIDE the interior launch instead of ahead of it
@@ -307,21 +338,63 @@ static int dist_phase_exchange(flk_field *f) {
     return FLK_OK;
 }
 
+// tiles, phase 2b: the left/right arrivals join the WRITE buffer; those in a border row are forwarded into the
+// lower/upper messages (the diagonal neighbours' birds travel in two hops, so every tile talks to four peers only)
+static int dist_phase_unpack_x(flk_field *f) {
+    flk_dist_state *d = f->dist;
+    CUDA_TRY(cudaStreamWaitEvent(f->stream, d->ev_copied, 0));
+    launch_unpack(f->g, f->s, f->stream, 0);
+    f->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(d->ev_fwd, f->stream));
+    return FLK_OK;
+}
+
+// tiles, phase 2c: the row-direction exchange
+static int dist_phase_exchange_y(flk_field *f) {
+    flk_dist_state *d = f->dist;
+    const size_t nbytes = xbuf_bytes(f->s.capx);
+    cudaStream_t cs = d->comm_stream;
+    CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_fwd, 0));
+    if (d->transport == 0) {
+        NCCL_TRY(g_nccl.GroupStart());
+        NCCL_TRY(g_nccl.Send(f->s.sendD, nbytes, kNcclUint8, d->down, d->comm, cs));
+        NCCL_TRY(g_nccl.Send(f->s.sendU, nbytes, kNcclUint8, d->up, d->comm, cs));
+        // order matters only for two tile rows (both messages come from the same peer): its sendD is my recvU
+        NCCL_TRY(g_nccl.Recv(f->s.recvU, nbytes, kNcclUint8, d->up, d->comm, cs));
+        NCCL_TRY(g_nccl.Recv(f->s.recvD, nbytes, kNcclUint8, d->down, d->comm, cs));
+        NCCL_TRY(g_nccl.GroupEnd());
+    } else {
+        flk_field *Dn = d->group[d->down], *Up = d->group[d->up];
+        CUDA_TRY(cudaStreamWaitEvent(cs, Dn->dist->ev_fwd, 0));
+        CUDA_TRY(cudaStreamWaitEvent(cs, Up->dist->ev_fwd, 0));
+        CUDA_TRY(cudaMemcpyPeerAsync(f->s.recvD, f->device, Dn->s.sendU, Dn->device, nbytes, cs));
+        CUDA_TRY(cudaMemcpyPeerAsync(f->s.recvU, f->device, Up->s.sendD, Up->device, nbytes, cs));
+    }
+    CUDA_TRY(cudaEventRecord(d->ev_copied_y, cs));
+    return FLK_OK;
+}
+
 // phase 3: arrivals join the WRITE buffer, then lazy_update
 static int dist_phase_finish(flk_field *f) {
     flk_dist_state *d = f->dist;
-    CUDA_TRY(cudaStreamWaitEvent(f->stream, d->ev_copied, 0));
+    const bool tiles = f->g.mode == 2;
+    CUDA_TRY(cudaStreamWaitEvent(f->stream, tiles ? d->ev_copied_y : d->ev_copied, 0));
     if (d->transport == 1) {
         // LOCAL: my neighbours read MY send buffers with their own copies; the next tick may not clear them before
         CUDA_TRY(cudaStreamWaitEvent(f->stream, d->group[d->left]->dist->ev_copied, 0));
         CUDA_TRY(cudaStreamWaitEvent(f->stream, d->group[d->right]->dist->ev_copied, 0));
+        if (tiles) {
+            CUDA_TRY(cudaStreamWaitEvent(f->stream, d->group[d->down]->dist->ev_copied_y, 0));
+            CUDA_TRY(cudaStreamWaitEvent(f->stream, d->group[d->up]->dist->ev_copied_y, 0));
+        }
     }
-    launch_unpack(f->g, f->s, f->stream);
+    launch_unpack(f->g, f->s, f->stream, tiles ? 1 : 0);
     f->launches += 1;
     CUDA_TRY(cudaGetLastError());
     // grid bounds only; validity is decided on the device.  The new READ population is at most the old bound plus
-    // both messages.
-    const uint64_t ub = (uint64_t)read_upper_bound(f) + 2ull * f->s.capx;
+    // the messages.
+    const uint64_t ub = (uint64_t)read_upper_bound(f) + (uint64_t)f->s.nrecv * f->s.capx;
     f->w_count = ub < f->cap ? ub : f->cap;
     int rc = enqueue_lazy_update(f, 0);
     f->n_read = f->cap;   // the host only keeps an upper bound (the exact count lives on the device)
@@ -340,6 +413,8 @@ static int dist_phase_finish(flk_field *f) {
 static int dist_tick(flk_field *f, uint64_t step, uint64_t seed, const float2 *d_inj, uint32_t n_inj, int identity) {
     int rc = dist_phase_step(f, step, seed, d_inj, n_inj, identity);
     if (!rc) rc = dist_phase_exchange(f);
+    if (!rc && f->g.mode == 2) rc = dist_phase_unpack_x(f);
+    if (!rc && f->g.mode == 2) rc = dist_phase_exchange_y(f);
     if (!rc) rc = dist_phase_finish(f);
     return rc;
 }
@@ -419,10 +494,18 @@ int flk_dist_create(float width, float height, float discretization, uint64_t ca
 
 int flk_dist_create_cols(float width, float height, float discretization, uint64_t capacity, int device, int rank,
                          int world, const uint8_t *id128, const int32_t *col_bounds, flk_field **out) {
+    return flk_dist_create_tiles(width, height, discretization, capacity, device, rank, world, id128, 1, col_bounds,
+                                 nullptr, out);
+}
+
+int flk_dist_create_tiles(float width, float height, float discretization, uint64_t capacity, int device, int rank,
+                          int world, const uint8_t *id128, int tile_rows, const int32_t *col_bounds,
+                          const int32_t *row_bounds, flk_field **out) {
     if (!out || !id128) return fail(FLK_E_INVALID, "null argument");
     int rc = nccl_load();
     if (rc) return rc;
-    rc = dist_field_new(width, height, discretization, capacity, device, rank, world, 0, out, col_bounds);
+    rc = dist_field_new(width, height, discretization, capacity, device, rank, world, 0, out, col_bounds, tile_rows,
+                        row_bounds);
     if (rc) return rc;
     ncclUniqueId id;
     memcpy(id.internal, id128, 128);
@@ -471,10 +554,17 @@ int flk_balance_columns(const float *x, uint64_t n, uint64_t stride, float width
 
 int flk_mgpu_create_cols(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
                          const int *devices, const int32_t *col_bounds, flk_field **out) {
+    return flk_mgpu_create_tiles(width, height, discretization, capacity_per_rank, n, devices, 1, col_bounds, nullptr, out);
+}
+
+int flk_mgpu_create_tiles(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
+                          const int *devices, int tile_rows, const int32_t *col_bounds, const int32_t *row_bounds,
+                          flk_field **out) {
     if (!out || !devices || n < 2) return fail(FLK_E_INVALID, "need n >= 2 devices");
     flk_field **grp = new flk_field *[n];
     for (int r = 0; r < n; ++r) {
-        int rc = dist_field_new(width, height, discretization, capacity_per_rank, devices[r], r, n, 1, &grp[r], col_bounds);
+        int rc = dist_field_new(width, height, discretization, capacity_per_rank, devices[r], r, n, 1, &grp[r], col_bounds,
+                                tile_rows, row_bounds);
         if (rc) {
             for (int q = 0; q < r; ++q) { grp[q]->dist->group = nullptr; flk_field_destroy(grp[q]); }
             delete[] grp;
@@ -500,15 +590,37 @@ int flk_mgpu_create_cols(float width, float height, float discretization, uint64
 
 int flk_dist_strip(const flk_field *f, int32_t *col0, int32_t *col1) {
     if (!f) return fail(FLK_E_INVALID, "null handle");
-    if (col0) *col0 = f->g.mode == 1 ? f->g.col0 : 0;
-    if (col1) *col1 = f->g.mode == 1 ? f->g.col0 + f->g.nown : f->g.mx;
+    if (col0) *col0 = f->g.mode != 0 ? f->g.col0 : 0;
+    if (col1) *col1 = f->g.mode != 0 ? f->g.col0 + f->g.nown : f->g.mx;
     return FLK_OK;
 }
 
+int flk_dist_tile(const flk_field *f, int32_t *col0, int32_t *col1, int32_t *row0, int32_t *row1) {
+    if (!f) return fail(FLK_E_INVALID, "null handle");
+    flk_dist_strip(f, col0, col1);
+    if (row0) *row0 = f->g.mode == 2 ? f->g.row0 : 0;
+    if (row1) *row1 = f->g.mode == 2 ? f->g.row0 + f->g.rown : f->g.my;
+    return FLK_OK;
+}
+
+static int cell_of(float v, float d) {   // same f32 arithmetic as the device binning
+    float q = std::floor(v / d);
+    int c = (q != q) ? 0 : (q >= 2147483648.0f ? 0x7fffffff : (q <= -2147483648.0f ? -0x7fffffff - 1 : (int)q));
+    return c < 0 ? 0 : c;
+}
+
 int flk_dist_owner(const flk_field *f, float x, float y, int32_t *rank) {
-    (void)y;
     if (!f || !rank) return fail(FLK_E_INVALID, "null argument");
-    if (f->g.mode != 1) { *rank = 0; return FLK_OK; }
+    if (f->g.mode == 2) {   // get_block_by_location on the tile grid; the slack column / row belong to column / row 0
+        const flk_dist_state *d = f->dist;
+        const int gc = cell_of(x, f->g.d), gr = cell_of(y, f->g.d);
+        int px = 0, py = 0;
+        if (gc < f->g.mx) for (int r = 0; r < d->Px; ++r) if (gc >= d->bounds[r] && gc < d->bounds[r + 1]) px = r;
+        if (gr < f->g.my) for (int r = 0; r < d->Py; ++r) if (gr >= d->rbounds[r] && gr < d->rbounds[r + 1]) py = r;
+        *rank = py * d->Px + px;
+        return FLK_OK;
+    }
+    if (f->g.mode == 0) { *rank = 0; return FLK_OK; }
     float q = std::floor(x / f->g.d);   // same f32 arithmetic as the device binning
     int gc = (q != q) ? 0 : (q >= 2147483648.0f ? 0x7fffffff : (q <= -2147483648.0f ? -0x7fffffff - 1 : (int)q));
     if (gc < 0) gc = 0;
@@ -523,7 +635,7 @@ int flk_dist_owner(const flk_field *f, float x, float y, int32_t *rank) {
 // publish the uploaded birds and build the first halo (state.rs:113-133)
 int flk_dist_commit(flk_field *f) {
     CHECK_HANDLE(f);
-    if (f->g.mode != 1) return flk_lazy_update(f);
+    if (f->g.mode == 0) return flk_lazy_update(f);
     if (f->dist->transport != 0) return fail(FLK_E_STATE, "use flk_mgpu_commit on an in-process group");
     int rc = flush_pending(f);
     if (rc) return rc;
@@ -538,7 +650,7 @@ int flk_dist_commit(flk_field *f) {
 
 int flk_dist_step(flk_field *f, uint64_t step, uint64_t seed, const float *injected_r, uint64_t n_injected) {
     CHECK_HANDLE(f);
-    if (f->g.mode != 1) {
+    if (f->g.mode == 0) {
         int rc = flk_step(f, step, seed, injected_r, n_injected);
         return rc ? rc : flk_lazy_update(f);
     }
@@ -583,6 +695,18 @@ static int mgpu_tick(flk_field **hs, int n, uint64_t step, uint64_t seed, const 
         CUDA_TRY(cudaSetDevice(hs[r]->device));
         int rc = dist_phase_exchange(hs[r]);
         if (rc) return rc;
+    }
+    if (hs[0]->g.mode == 2) {
+        for (int r = 0; r < n; ++r) {
+            CUDA_TRY(cudaSetDevice(hs[r]->device));
+            int rc = dist_phase_unpack_x(hs[r]);
+            if (rc) return rc;
+        }
+        for (int r = 0; r < n; ++r) {
+            CUDA_TRY(cudaSetDevice(hs[r]->device));
+            int rc = dist_phase_exchange_y(hs[r]);
+            if (rc) return rc;
+        }
     }
     for (int r = 0; r < n; ++r) {
         CUDA_TRY(cudaSetDevice(hs[r]->device));
@@ -637,9 +761,20 @@ int flk_mgpu_run(flk_field **hs, int n, uint64_t first_step, uint64_t n_steps, u
 int flk_dist_num_owned(flk_field *f, uint64_t *n) {
     CHECK_HANDLE(f);
     if (!n) return fail(FLK_E_INVALID, "n is null");
-    if (f->g.mode != 1) { *n = f->n_read; return FLK_OK; }
+    if (f->g.mode == 0) { *n = f->n_read; return FLK_OK; }
     int rc = dist_check_errors(f);
     if (rc) return rc;
+    if (f->g.mode == 2) {   // tiles: count by compaction (owned cells are not an index range)
+        uint32_t *d_cnt = reinterpret_cast<uint32_t *>(f->scratch + ((f->cap * 20 + 15) & ~(uint64_t)15) + 96);
+        uint32_t h = 0;
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, f->stream));
+        launch_compact_owned(f->g, f->s, (uint32_t)f->cap, nullptr, nullptr, nullptr, d_cnt, f->stream);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&h, d_cnt, 4, cudaMemcpyDeviceToHost, f->stream));
+        CUDA_TRY(cudaStreamSynchronize(f->stream));
+        *n = h;
+        return FLK_OK;
+    }
     // owned birds = cells of local columns [1, nown] plus the slack column
     uint32_t b[4];
     const uint32_t dh = (uint32_t)f->g.dh, nown = (uint32_t)f->g.nown;
@@ -654,9 +789,30 @@ int flk_dist_num_owned(flk_field *f, uint64_t *n) {
 // snapshot of the birds this rank OWNS (ghost copies excluded), (cell, id) order
 static int dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n, bool sync) {
     CHECK_HANDLE(f);
-    if (f->g.mode != 1) return sync ? flk_snapshot(f, id, loc, last_d, n) : flk_snapshot_async(f, id, loc, last_d, n);
+    if (f->g.mode == 0) return sync ? flk_snapshot(f, id, loc, last_d, n) : flk_snapshot_async(f, id, loc, last_d, n);
     int rc = dist_check_errors(f);
     if (rc) return rc;
+    if (f->g.mode == 2) {   // tiles: compact the owned birds into the scratch block, then copy
+        const uint64_t cap = f->cap;
+        uint32_t *d_id = reinterpret_cast<uint32_t *>(f->scratch);
+        float2 *d_loc = reinterpret_cast<float2 *>(f->scratch + ((cap * 4 + 7) & ~(uint64_t)7));
+        float2 *d_ld = d_loc + cap;
+        uint32_t *d_cnt = reinterpret_cast<uint32_t *>(f->scratch + ((cap * 20 + 15) & ~(uint64_t)15) + 96);
+        uint32_t h = 0;
+        CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, f->stream));
+        launch_compact_owned(f->g, f->s, (uint32_t)cap, id ? d_id : nullptr, loc ? d_loc : nullptr, last_d ? d_ld : nullptr,
+                             d_cnt, f->stream);
+        f->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(&h, d_cnt, 4, cudaMemcpyDeviceToHost, f->stream));
+        CUDA_TRY(cudaStreamSynchronize(f->stream));
+        if (n) *n = h;
+        if (h && id) CUDA_TRY(cudaMemcpyAsync(id, d_id, (uint64_t)h * 4, cudaMemcpyDeviceToHost, f->stream));
+        if (h && loc) CUDA_TRY(cudaMemcpyAsync(loc, d_loc, (uint64_t)h * 8, cudaMemcpyDeviceToHost, f->stream));
+        if (h && last_d) CUDA_TRY(cudaMemcpyAsync(last_d, d_ld, (uint64_t)h * 8, cudaMemcpyDeviceToHost, f->stream));
+        if (sync) CUDA_TRY(cudaStreamSynchronize(f->stream));
+        return FLK_OK;
+    }
     uint32_t b[4];
     const uint32_t dh = (uint32_t)f->g.dh, nown = (uint32_t)f->g.nown;
     const uint32_t idx[4] = {1 * dh, (nown + 1) * dh, (nown + 2) * dh, (nown + 3) * dh};

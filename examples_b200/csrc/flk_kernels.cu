@@ -19,15 +19,22 @@ namespace flk {
 // neighbour window enumeration: calls f(s, e) for each run [s,e) of READ indices, in the reference's
 // query order (x-outer, y-inner, bag order; SURVEY Appendix B "relax query")
 // ------------------------------------------------------------------------------------------------
-template <class F>
+template <int ROWS = -1, class F>   // ROWS: 0 = rows not split (compiled out), 1 = split, -1 = decided at run time
 __device__ __forceinline__ void for_each_window_run(const Geom &g, const uint32_t *__restrict__ cell_start,
                                                     int lc, int cy, int k, F &&f) {
+    const bool rows_split = ROWS < 0 ? g.mode == 2 : ROWS != 0;
     for (int ox = -k; ox <= k; ++ox) {
         const int col = window_col(g, lc, ox);
         if (col < 0) continue;
         int r0 = cy - k, r1 = cy + k;
         bool contiguous;
-        if (g.toroidal) {
+        if (rows_split) {
+            // cy is a LOCAL row; the ghost rows materialise the wrap.  Slack row (global row my): window {my-1, 0, 1}
+            if (cy == g.rown + 2) { r0 = 0; r1 = 2 * k; }
+            r0 = max(r0, 0);
+            r1 = min(r1, g.rown + 1);
+            contiguous = true;
+        } else if (g.toroidal) {
             contiguous = (r0 >= 0) && (r1 < g.my);
         } else {
             r0 = max(r0, 0);
@@ -60,7 +67,7 @@ struct Acc {
 
 // Generic form: any window width, wrap, seam, either query.  Used by border birds and by the exact-distance query.
 // MATH: 0 = exact (division guarded per pair, div2_rn); 1 = fast (approximate reciprocal)
-template <bool RELAX, int MATH>
+template <bool RELAX, int MATH, int ROWS = -1>
 __device__ __forceinline__ void accumulate_window(const Geom &g, const Params &p, const Store &s, const Rec &me,
                                                   uint32_t i, int lc, int cy, Acc &acc) {
     const float W = g.W, H = g.H;
@@ -69,7 +76,7 @@ __device__ __forceinline__ void accumulate_window(const Geom &g, const Params &p
     uint32_t nvec = 0;
     int count = 0;
     const float4 *__restrict__ rec = reinterpret_cast<const float4 *>(s.rec);
-    for_each_window_run(g, s.cell_start, lc, cy, p.k, [&](uint32_t rs, uint32_t re) {
+    for_each_window_run<ROWS>(g, s.cell_start, lc, cy, p.k, [&](uint32_t rs, uint32_t re) {
         uint32_t j = rs;
         while (true) {
             // the caller itself is part of the query result and skipped by id (bird.rs:53): split the run at i
@@ -187,27 +194,34 @@ __device__ __forceinline__ void xbuf_append(const Store &s, uint8_t *buf, const 
     }
 }
 
-template <bool NOPAY = false>
+template <bool NOPAY = false, int ROWS = -1>   // ROWS: 0 = rows not split (compiled out), 1 = split, -1 = decided at run time
 __device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, const Rec &out, uint32_t id, uint32_t w,
                                                bool d_ok, const Recip &Rd, uint32_t src) {
     // Field2D<O>: whatever else the object carries moves with it (set_object_location stores the whole object)
     if (!NOPAY)
         for (uint32_t k = 0; k < s.pw; ++k) s.tpay[(size_t)w * s.pw + k] = s.pay[(size_t)src * s.pw + k];
     const int ncx = d_ok ? cell_coord_fast(out.x, Rd, g.mx + 1) : cell_coord(out.x, g.d, g.mx + 1);
-    const int ncy = d_ok ? cell_coord_fast(out.y, Rd, g.dh) : cell_coord(out.y, g.d, g.dh);
+    const bool rows = ROWS < 0 ? g.mode == 2 : ROWS != 0;
+    const int nrows = rows ? g.dhg : g.dh;   // the same number unless the rows are split
+    const int ncy = d_ok ? cell_coord_fast(out.y, Rd, nrows) : cell_coord(out.y, g.d, nrows);
     const int nlc = local_col(g, ncx);
+    const int nlr = rows ? local_row(g, ncy) : ncy;
     uint32_t key = KEY_INVALID, slot = 0;
-    if (nlc != FLK_DROP) {
-        key = (uint32_t)nlc * (uint32_t)g.dh + (uint32_t)ncy;
+    if (nlc != FLK_DROP && (!rows || nlr != FLK_DROP)) {
+        key = (uint32_t)nlc * (uint32_t)g.dh + (uint32_t)nlr;
         slot = atomicAdd(s.cnt + key, 1u);
     }
     reinterpret_cast<float4 *>(s.trec)[w] = make_float4(out.x, out.y, out.ldx, out.ldy);
     s.tid[w] = id;
     s.tkey[w] = key;
     s.tslot[w] = slot;
-    if (g.mode == 1) {
+    if (g.mode != 0) {
         if (nlc == 0 || nlc == 1) xbuf_append(s, s.sendL, out, id);
         if (nlc == g.nown || nlc == g.nown + 1 || (nlc == FLK_DROP && ncx >= g.mx)) xbuf_append(s, s.sendR, out, id);
+    }
+    if (rows) {   // same rule along y; a corner successor goes into both (and is forwarded diagonally, k_unpack)
+        if (nlr == 0 || nlr == 1) xbuf_append(s, s.sendD, out, id);
+        if (nlr == g.rown || nlr == g.rown + 1 || (nlr == FLK_DROP && ncy >= g.my)) xbuf_append(s, s.sendU, out, id);
     }
 }
 
@@ -238,7 +252,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 constexpr int TILE_CAP = 256;   // records staged per window column (4 KB); 3 columns = 12 KB per CTA
 
 // everything of Bird::step after the neighbour loop (bird.rs:73-145) + set_object_location
-template <int MATH, bool NOPAY = false>
+template <int MATH, bool NOPAY = false, int ROWS = -1>
 __device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, const Store &s, const StepArgs &a, const Rec &me,
                                             uint32_t my_id, uint32_t w, const Acc &acc, bool d_ok, const Recip &Rd,
                                             uint32_t src) {
@@ -310,7 +324,7 @@ __device__ __forceinline__ void finish_bird(const Geom &g, const Params &p, cons
     out.x = toroidal_transform(__fadd_rn(me.x, dx), W);                              // :137
     out.y = toroidal_transform(__fadd_rn(me.y, dy), H);                              // :138
 
-    emit_successor<NOPAY>(g, s, out, my_id, w, d_ok, Rd, src);   // :142-144
+    emit_successor<NOPAY, ROWS>(g, s, out, my_id, w, d_ok, Rd, src);   // :142-144
 }
 
 // interior accumulation out of the CTA's shared-memory tile (same order, same arithmetic as accumulate_interior)
@@ -440,24 +454,30 @@ __device__ __forceinline__ void accumulate_run_smem(const float4 *tile, uint32_t
 // Everything that is not the common case — a bird next to the seam, a CTA that straddles two cell columns, a window
 // wider than 3x3, the exact-distance query, a non-toroidal field — finishes its bird here.  Kept out of line so
 // that the register allocation of the tile path in k_step is not shaped by these loops (same arithmetic, same order).
-template <bool RELAX, int MATH>
+template <bool RELAX, int MATH, bool TILES>
 __device__ __noinline__ void step_bird_general(const Geom &g, const Params &p, const Store &s, const StepArgs &a,
                                                uint32_t i, uint32_t w) {
     const Rec me = s.rec[i];
     const uint32_t my_id = s.ids[i];
     const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
     const Recip Rd = make_recip(g.d);
+    if (a.identity) {   // dist commit: re-stage the bird unchanged (builds the first halo)
+        emit_successor<false, TILES ? 1 : 0>(g, s, me, my_id, w, d_ok, Rd, i);
+        return;
+    }
     const int gcx = d_ok ? cell_coord_fast(me.x, Rd, g.mx + 1) : cell_coord(me.x, g.d, g.mx + 1);
-    const int cy = d_ok ? cell_coord_fast(me.y, Rd, g.dh) : cell_coord(me.y, g.d, g.dh);
+    const int nrows = TILES ? g.dhg : g.dh;
+    const int cy = d_ok ? cell_coord_fast(me.y, Rd, nrows) : cell_coord(me.y, g.d, nrows);
     const int lc = local_col(g, gcx);
+    const int lr = TILES ? local_row(g, cy) : cy;   // row of the local cell arrays (== cy unless the rows are split)
     Acc acc;
     // Birds whose 3x3 window cannot touch the seam never take the |a-b| > dim/2 branch of toroidal_distance:
     // cells are < 2d apart and dim >= 6d, so the plain difference is the toroidal one (exactly).
     const bool interior = g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && gcx >= 1 && gcx <= g.mx - 2 &&
                           cy >= 1 && cy <= g.my - 2 && d_ok;
-    if (interior && RELAX) accumulate_interior<MATH>(g, s, me, i, lc, cy, acc);
-    else accumulate_window<RELAX, MATH>(g, p, s, me, i, lc, cy, acc);
-    finish_bird<MATH>(g, p, s, a, me, my_id, w, acc, d_ok, Rd, i);
+    if (interior && RELAX) accumulate_interior<MATH>(g, s, me, i, lc, lr, acc);
+    else accumulate_window<RELAX, MATH, TILES ? 1 : 0>(g, p, s, me, i, lc, lr, acc);
+    finish_bird<MATH, false, TILES ? 1 : 0>(g, p, s, a, me, my_id, w, acc, d_ok, Rd, i);
 }
 
 // k_step: one thread per READ bird.  TILE = stage the CTA's three window-column runs in shared memory with TMA bulk
@@ -467,14 +487,15 @@ __device__ __noinline__ void step_bird_general(const Geom &g, const Params &p, c
 #ifndef FLK_STEP_MINBLOCKS
 #define FLK_STEP_MINBLOCKS 9   // 56 registers; with the prefetching loop: 0.851 ms (9), 0.856 (10), 0.884 (12)
 #endif
-template <bool RELAX, int MATH, bool TILE, bool FASTG>
+// TILES = the rows are split too (mode 2): the row of the local cell arrays differs from the global row
+template <bool RELAX, int MATH, bool TILE, bool FASTG, bool TILES = false>
 __global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS)
 k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const __grid_constant__ Store s,
        const __grid_constant__ StepArgs a) {
     __shared__ __align__(128) float4 tile_s[TILE ? 3 * TILE_CAP + 1 : 1];
     float4 *const tile[3] = {tile_s, tile_s + (TILE ? TILE_CAP : 0), tile_s + (TILE ? 2 * TILE_CAP : 0)};
     __shared__ __align__(8) uint64_t bar;
-    __shared__ int shc[5];
+    __shared__ int shc[TILES ? 7 : 5];
 
     // cell_start[0] is 0 by construction: a whole-field launch knows its first bird without a load, so the bird's own
     // record (read speculatively: any index below cap is allocated) is in flight together with the range end
@@ -496,29 +517,33 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
         const Recip Rd = make_recip(g.d);
         const uint32_t dh = (uint32_t)g.dh;
         float mex = 0.0f, mey = 0.0f;
-        int gcx = 0, cy = 0, lc = 0;
+        int gcx = 0, cy = 0, lc = 0, lr = 0;   // cy: global row (seam test); lr: row of the local cell arrays
         if (valid) {
             mex = xy.x; mey = xy.y;
             gcx = d_ok ? cell_coord_fast(mex, Rd, g.mx + 1) : cell_coord(mex, g.d, g.mx + 1);
-            cy = d_ok ? cell_coord_fast(mey, Rd, g.dh) : cell_coord(mey, g.d, g.dh);
+            cy = d_ok ? cell_coord_fast(mey, Rd, TILES ? g.dhg : g.dh) : cell_coord(mey, g.d, TILES ? g.dhg : g.dh);
             lc = local_col(g, gcx);
+            lr = TILES ? local_row(g, cy) : cy;
         }
         const uint32_t last = min(first + blockDim.x, hi) - 1;
         if (threadIdx.x == 0) {
             shc[0] = lc; shc[1] = cy; shc[4] = gcx;
+            if (TILES) shc[5] = lr;
             mbar_init(&bar, 1);
         }
-        if (i == last) { shc[2] = lc; shc[3] = cy; }
+        if (i == last) { shc[2] = lc; shc[3] = cy; if (TILES) shc[6] = lr; }
         __syncthreads();
         const int lcA = shc[0], cyA = shc[1], lcB = shc[2], cyB = shc[3], gcxA = shc[4];
+        const int lrA = TILES ? shc[5] : cyA, lrB = TILES ? shc[6] : cyB;
         bool eligible = (FASTG || (RELAX && !a.identity && g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && d_ok &&
                                    s.pw == 0)) &&
                         lcA == lcB && gcxA >= 1 && gcxA <= g.mx - 2 && cyA >= 1 && cyB <= g.my - 2 && cyA <= cyB &&
-                        (g.mode == 0 || (lcA >= 1 && lcA <= g.nown));
+                        (g.mode == 0 || (lcA >= 1 && lcA <= g.nown)) &&
+                        (!TILES || (lrA >= 1 && lrB <= g.rown && lrA <= lrB));
         uint32_t sA0 = 0, sA1 = 0, sA2 = 0, len0 = 0, len1 = 0, len2 = 0;
         if (eligible) {
-            const uint32_t *cs = s.cell_start + ((uint32_t)(lcA - 1) * dh + (uint32_t)(cyA - 1));
-            const uint32_t span = (uint32_t)(cyB - cyA) + 3u;
+            const uint32_t *cs = s.cell_start + ((uint32_t)(lcA - 1) * dh + (uint32_t)(lrA - 1));
+            const uint32_t span = (uint32_t)(lrB - lrA) + 3u;
             sA0 = __ldg(cs);          len0 = __ldg(cs + span) - sA0;
             sA1 = __ldg(cs + dh);     len1 = __ldg(cs + dh + span) - sA1;
             sA2 = __ldg(cs + 2 * dh); len2 = __ldg(cs + 2 * dh + span) - sA2;
@@ -535,7 +560,7 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
             // this bird's three runs, as offsets into the staged column runs (loads in flight during the copy)
             uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0, a2 = 0, b2 = 0;
             if (valid) {
-                const uint32_t *cs = s.cell_start + ((uint32_t)(lc - 1) * dh + (uint32_t)(cy - 1));
+                const uint32_t *cs = s.cell_start + ((uint32_t)(lc - 1) * dh + (uint32_t)(lr - 1));
                 a0 = __ldg(cs);          b0 = __ldg(cs + 3);
                 a1 = __ldg(cs + dh);     b1 = __ldg(cs + dh + 3);
                 a2 = __ldg(cs + 2 * dh); b2 = __ldg(cs + 2 * dh + 3);
@@ -563,27 +588,22 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
             // through the loops
             const float2 ld = *(reinterpret_cast<const float2 *>(s.rec + i) + 1);
             const Rec me = Rec{mex, mey, ld.x, ld.y};
-            finish_bird<MATH, FASTG>(g, p, s, a, me, s.ids[i], w, acc, d_ok, Rd, i);
+            finish_bird<MATH, FASTG, TILES ? 1 : 0>(g, p, s, a, me, s.ids[i], w, acc, d_ok, Rd, i);
             return;
         }
     }
     if (!valid) return;
-    if (g.mode == 1) {
+    if (g.mode != 0) {
         const Rec me = s.rec[i];
-        const int gcx = cell_coord(me.x, g.d, g.mx + 1);
-        const int lc = local_col(g, gcx);
-        if (lc == 0 || lc == g.nown + 1) {
+        const int lc = local_col(g, cell_coord(me.x, g.d, g.mx + 1));
+        const int lr = TILES ? local_row(g, cell_coord(me.y, g.d, g.dhg)) : 1;
+        if (lc == 0 || lc == g.nown + 1 || (TILES && (lr == 0 || lr == g.rown + 1))) {
             // ghost copy (flockers_mpi: received_neighbors): stepped by its owner, dropped here
             s.tkey[w] = KEY_INVALID;
             return;
         }
     }
-    if (a.identity) {
-        const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
-        emit_successor(g, s, s.rec[i], s.ids[i], w, d_ok, make_recip(g.d), i);
-        return;
-    }
-    step_bird_general<RELAX, MATH>(g, p, s, a, i, w);
+    step_bird_general<RELAX, MATH, TILES>(g, p, s, a, i, w);   // also the identity pass (re-stage unchanged)
 }
 
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
@@ -595,7 +615,16 @@ void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs 
     const bool fastg = p.relax && g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && g.d >= 0x1p-20f && g.d <= 4096.0f &&
                        s.pw == 0 && !a.identity;
 #define FLK_LAUNCH(R, M, T, F) k_step<R, M, T, F><<<grid, block, 0, st>>>(g, p, s, a)
-    if (p.relax) {
+#define FLK_LAUNCH_T(R, M, T) k_step<R, M, T, false, true><<<grid, block, 0, st>>>(g, p, s, a)
+    if (g.mode == 2) {   // rows split: every variant is the TILES instantiation (ghost rows, local row arithmetic)
+        if (p.relax) {
+            if (a.math_mode == 1) { if (tile) FLK_LAUNCH_T(true, 1, true); else FLK_LAUNCH_T(true, 1, false); }
+            else { if (tile) FLK_LAUNCH_T(true, 0, true); else FLK_LAUNCH_T(true, 0, false); }
+        } else {
+            if (a.math_mode == 1) FLK_LAUNCH_T(false, 1, false);
+            else FLK_LAUNCH_T(false, 0, false);
+        }
+    } else if (p.relax) {
         if (a.math_mode == 1) {
             if (tile && fastg) FLK_LAUNCH(true, 1, true, true);
             else if (tile) FLK_LAUNCH(true, 1, true, false);
@@ -610,6 +639,7 @@ void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs 
         else FLK_LAUNCH(false, 0, false, false);
     }
 #undef FLK_LAUNCH
+#undef FLK_LAUNCH_T
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -622,13 +652,14 @@ __global__ void __launch_bounds__(256) k_ingest(const Geom g, const Store s, uin
     if (j >= n) return;
     const float2 l = loc[j], d = ld[j];
     const int cx = cell_coord(l.x, g.d, g.mx + 1);
-    const int cy = cell_coord(l.y, g.d, g.dh);
+    const int cy = local_row(g, cell_coord(l.y, g.d, g.dhg));
     int lc = local_col(g, cx);
-    // strip mode: only birds this rank owns are accepted (flockers_mpi/src/model/state.rs:75-85); ghosts arrive
+    // strip / tile mode: only birds this rank owns are accepted (flockers_mpi/src/model/state.rs:75-85); ghosts arrive
     // through the halo exchange
-    if (owned_only && g.mode == 1 && (lc == 0 || lc == g.nown + 1)) lc = FLK_DROP;
+    if (owned_only && g.mode != 0 && (lc == 0 || lc == g.nown + 1)) lc = FLK_DROP;
+    if (owned_only && g.mode == 2 && (cy == 0 || cy == g.rown + 1)) lc = FLK_DROP;
     uint32_t key = KEY_INVALID, slot = 0;
-    if (lc != FLK_DROP) {
+    if (lc != FLK_DROP && cy != FLK_DROP) {
         key = (uint32_t)lc * (uint32_t)g.dh + (uint32_t)cy;
         slot = atomicAdd(s.cnt + key, 1u);
     }
@@ -654,7 +685,7 @@ __global__ void __launch_bounds__(256) k_ingest_dense(const Geom g, const Store 
     if (j >= n) return;
     const float4 r = rec4[j];
     const int cx = cell_coord(r.x, g.d, g.mx + 1);
-    const int cy = cell_coord(r.y, g.d, g.dh);
+    const int cy = cell_coord(r.y, g.d, g.dhg);
     const uint32_t key = (uint32_t)cx * (uint32_t)g.dh + (uint32_t)cy;
     const uint32_t slot = atomicAdd(s.cnt + key, 1u);
     reinterpret_cast<float4 *>(s.trec)[base + j] = r;
@@ -675,32 +706,67 @@ void launch_ingest_dense(const Geom &g, const Store &s, uint32_t n, uint32_t id0
 // buffer at [cap, cap+capx) (from the left) and [cap+capx, cap+2capx) (from the right)
 // (flockers_mpi/src/model/state.rs:128-130,167-174)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_unpack(const Geom g, const Store s) {
+__global__ void __launch_bounds__(256) k_unpack(const Geom g, const Store s, int phase) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 2 * s.capx) return;
     const int side = t >= s.capx;
     const uint32_t j = side ? t - s.capx : t;
-    uint8_t *buf = side ? s.recvR : s.recvL;
+    uint8_t *buf = phase == 0 ? (side ? s.recvR : s.recvL) : (side ? s.recvU : s.recvD);
     const uint32_t n = min(reinterpret_cast<const XHdr *>(buf)->count, s.capx);
-    if (j >= n || t >= 2 * s.capx) return;
+    if (j >= n) return;
     const float4 r = reinterpret_cast<const float4 *>(xbuf_rec(buf))[j];
     const uint32_t id = xbuf_id(buf, s.capx)[j];
     const int cx = cell_coord(r.x, g.d, g.mx + 1);
-    const int cy = cell_coord(r.y, g.d, g.dh);
+    const int cy = cell_coord(r.y, g.d, g.dhg);
     const int lc = local_col(g, cx);
+    const int lr = local_row(g, cy);
     uint32_t key = KEY_INVALID, slot = 0;
-    if (lc != FLK_DROP) {
-        key = (uint32_t)lc * (uint32_t)g.dh + (uint32_t)cy;
+    if (lc != FLK_DROP && lr != FLK_DROP) {
+        key = (uint32_t)lc * (uint32_t)g.dh + (uint32_t)lr;
         slot = atomicAdd(s.cnt + key, 1u);
     }
-    const uint32_t w = s.cap + t;
+    const uint32_t w = s.cap + (uint32_t)phase * 2u * s.capx + t;
     reinterpret_cast<float4 *>(s.trec)[w] = r;
     s.tid[w] = id;
     s.tkey[w] = key;
     s.tslot[w] = slot;
+    if (g.mode == 2 && phase == 0) {
+        // tiles: a bird that came in from the left/right neighbour and sits in one of my border rows is a ghost (or a
+        // migrant) of my lower/upper neighbour too, whose columns are mine: forward it (the diagonal hop)
+        const Rec rr = Rec{r.x, r.y, r.z, r.w};
+        if (lr == 0 || lr == 1) xbuf_append(s, s.sendD, rr, id);
+        if (lr == g.rown || lr == g.rown + 1 || (lr == FLK_DROP && cy >= g.my)) xbuf_append(s, s.sendU, rr, id);
+    }
 }
 
-void launch_unpack(const Geom &g, const Store &s, cudaStream_t st) {
-    k_unpack<<<(2 * s.capx + 255) / 256, 256, 0, st>>>(g, s);
+void launch_unpack(const Geom &g, const Store &s, cudaStream_t st, int phase) {
+    k_unpack<<<(2 * s.capx + 255) / 256, 256, 0, st>>>(g, s, phase);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_compact_owned (tiles): the birds a tile owns — columns 1..nown (+ slack column) x rows 1..rown (+ slack row) — are
+// scattered over the READ buffer; append them to the output arrays (order: arrival; callers sort by id)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_compact_owned(const Geom g, const Store s, uint32_t n_upper, uint32_t *out_id,
+                                                       float2 *out_loc, float2 *out_ld, uint32_t *counter) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_upper || i >= *s.n_read_dev) return;
+    const float4 r = reinterpret_cast<const float4 *>(s.rec)[i];
+    const int lc = local_col(g, cell_coord(r.x, g.d, g.mx + 1));
+    const int lr = local_row(g, cell_coord(r.y, g.d, g.dhg));
+    const bool col_owned = (lc >= 1 && lc <= g.nown) || lc == g.nown + 2;
+    const bool row_owned = g.mode != 2 || (lr >= 1 && lr <= g.rown) || lr == g.rown + 2;
+    if (!col_owned || !row_owned) return;
+    const uint32_t k = atomicAdd(counter, 1u);
+    if (out_id) out_id[k] = s.ids[i];
+    if (out_loc) out_loc[k] = make_float2(r.x, r.y);
+    if (out_ld) out_ld[k] = make_float2(r.z, r.w);
+}
+
+void launch_compact_owned(const Geom &g, const Store &s, uint32_t n_upper, uint32_t *out_id, float2 *out_loc, float2 *out_ld,
+                          uint32_t *counter, cudaStream_t st) {
+    if (n_upper == 0) return;
+    k_compact_owned<<<(n_upper + 255) / 256, 256, 0, st>>>(g, s, n_upper, out_id, out_loc, out_ld, counter);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -801,9 +867,10 @@ __global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n, uint
             if (i >= *s.n_read_dev) return;
         } else {
             const uint32_t t = i - s.cap;
-            if (t >= 2 * s.capx) return;
-            const uint8_t *buf = t >= s.capx ? s.recvR : s.recvL;
-            if ((t >= s.capx ? t - s.capx : t) >= min(reinterpret_cast<const XHdr *>(buf)->count, s.capx)) return;
+            if (t >= s.nrecv * s.capx) return;
+            const uint32_t b = t / s.capx;
+            const uint8_t *buf = b == 0 ? s.recvL : (b == 1 ? s.recvR : (b == 2 ? s.recvD : s.recvU));
+            if (t - b * s.capx >= min(reinterpret_cast<const XHdr *>(buf)->count, s.capx)) return;
         }
     } else if (i >= n) {
         return;
@@ -861,7 +928,7 @@ void launch_scatter(const Store &s, uint32_t n, int dist, cudaStream_t st) {
         // stepped slots [0, n) (n = host upper bound of the READ population), then the two receive regions
         const uint32_t nn = n < s.cap ? n : s.cap;
         if (nn) k_scatter4<<<((nn + 3) / 4 + 255) / 256, 256, 0, st>>>(s, nn, 1);
-        k_scatter<true><<<(2 * s.capx + 255) / 256, 256, 0, st>>>(s, 2 * s.capx, s.cap);
+        k_scatter<true><<<(s.nrecv * s.capx + 255) / 256, 256, 0, st>>>(s, s.nrecv * s.capx, s.cap);
         return;
     }
     if (n == 0) return;
@@ -1021,11 +1088,11 @@ __global__ void __launch_bounds__(128) k_query(const Geom g, const Store s, uint
     if (dist > 0.0f) {
         const int k = __float2int_rz(floorf(__fdiv_rn(dist, g.d)));
         const int gcx = cell_coord(l.x, g.d, g.mx + 1);
-        const int cy = cell_coord(l.y, g.d, g.dh);
+        const int cy = local_row(g, cell_coord(l.y, g.d, g.dhg));   // row of the local cell arrays
         const int lc = local_col(g, gcx);
         const float halfW = __fdiv_rn(g.W, 2.0f), halfH = __fdiv_rn(g.H, 2.0f);
         uint32_t *dst = FILL ? out + offsets[q] : nullptr;
-        if (lc != FLK_DROP) {
+        if (lc != FLK_DROP && cy != FLK_DROP) {
             for_each_window_run(g, s.cell_start, lc, cy, k, [&](uint32_t rs, uint32_t re) {
                 for (uint32_t j = rs; j < re; ++j) {
                     if (!relax) {

@@ -30,6 +30,9 @@ struct Store {
     // strip decomposition only: fixed-capacity exchange buffers, XHdr | Rec[capx] | id[capx]
     uint32_t capx;
     uint8_t *sendL, *sendR, *recvL, *recvR;
+    // tiles (mode 2) add the row direction; received birds occupy WRITE slots [cap, cap + nrecv*capx)
+    uint8_t *sendD, *sendU, *recvD, *recvU;
+    uint32_t nrecv;        // 2 strips, 4 tiles
 };
 
 constexpr uint32_t ERR_CAPACITY = 1u;   // more objects than `cap` after an exchange
@@ -62,7 +65,12 @@ void launch_ingest_dense(const Geom &g, const Store &s, uint32_t n, uint32_t id0
                          cudaStream_t st);
 void launch_gather_dense(const Store &s, uint32_t n_upper, uint32_t id0, uint32_t n, float4 *out, uint32_t *outside,
                          cudaStream_t st);
-void launch_unpack(const Geom &g, const Store &s, cudaStream_t st);
+// phase 0: messages from the left/right neighbours (tiles: arrivals in a border row are forwarded to the lower/upper
+// neighbour's message); phase 1 (tiles): messages from the lower/upper neighbours
+void launch_unpack(const Geom &g, const Store &s, cudaStream_t st, int phase = 0);
+// tiles: the birds this rank owns are not an index range of the READ buffer: compact them (any of the outputs may be null)
+void launch_compact_owned(const Geom &g, const Store &s, uint32_t n_upper, uint32_t *out_id, float2 *out_loc, float2 *out_ld,
+                          uint32_t *counter, cudaStream_t st);
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st);
 // exclusive scan of cnt -> cell_start, zeroing cnt; 3 launches

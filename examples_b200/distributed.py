@@ -61,6 +61,12 @@ class _StripField(Field2D):
         check(self._L.flk_dist_strip(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def tile(self) -> tuple[int, int, int, int]:
+        """global cell range (col0, col1, row0, row1) this rank owns (strips: every row)"""
+        a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        check(self._L.flk_dist_tile(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
     def owner(self, x: float, y: float) -> int:
         r = C.c_int32()
         check(self._L.flk_dist_owner(self._h, x, y, C.byref(r)))
@@ -99,6 +105,7 @@ class _StripField(Field2D):
         return ids[:n], loc[:n], ld[:n]
 
     def binning(self):
+        """LOCAL binning: (columns owned + 3) x dh cells, dh = local rows (tiles: rows owned + 3)"""
         ncell = (self.strip()[1] - self.strip()[0] + 3) * self.dh
         cs = np.zeros(ncell + 1, dtype=np.uint32)
         n = self.num_objects()
@@ -111,7 +118,7 @@ class DistField2D(_StripField):
     """One strip of the torus on this process's GPU; collective calls must be made by every rank."""
 
     def __init__(self, width, height, discretization=DISCRETIZATION, capacity=1 << 20, device=0, rank=0, world=1,
-                 col_bounds=None):
+                 col_bounds=None, tile_rows=1, row_bounds=None):
         import torch
         import torch.distributed as dist
         self._L = _lib.load()
@@ -126,8 +133,9 @@ class DistField2D(_StripField):
         dist.broadcast(uid, src=0)
         raw = (C.c_uint8 * 128)(*uid.cpu().tolist())
         cb = None if col_bounds is None else np.ascontiguousarray(col_bounds, dtype=np.int32)
-        check(self._L.flk_dist_create_cols(width, height, discretization, capacity, device, rank, world, raw, _vp(cb),
-                                           C.byref(self._h)))
+        rb = None if row_bounds is None else np.ascontiguousarray(row_bounds, dtype=np.int32)
+        check(self._L.flk_dist_create_tiles(width, height, discretization, capacity, device, rank, world, raw, tile_rows,
+                                            _vp(cb), _vp(rb), C.byref(self._h)))
         self.width, self.height, self.discretization, self.toroidal = width, height, discretization, True
         self.capacity, self.rank, self.world = capacity, rank, world
         dw, dh, mx, my = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
@@ -153,20 +161,22 @@ class MgpuGroup:
     the strip logic is exercised on a single GPU)."""
 
     def __init__(self, width, height, discretization=DISCRETIZATION, capacity_per_rank=1 << 20, devices=(0, 0),
-                 col_bounds=None):
+                 col_bounds=None, tile_rows=1, row_bounds=None):
         self._L = _lib.load()
         n = len(devices)
         self.n = n
         self._arr = (C.c_void_p * n)()
         devs = (C.c_int * n)(*devices)
         cb = None if col_bounds is None else np.ascontiguousarray(col_bounds, dtype=np.int32)
-        check(self._L.flk_mgpu_create_cols(width, height, discretization, capacity_per_rank, n, devs, _vp(cb), self._arr))
+        rb = None if row_bounds is None else np.ascontiguousarray(row_bounds, dtype=np.int32)
+        check(self._L.flk_mgpu_create_tiles(width, height, discretization, capacity_per_rank, n, devs, tile_rows, _vp(cb),
+                                            _vp(rb), self._arr))
         self.fields = []
         for r in range(n):
             f = _StripField._adopt(C.c_void_p(self._arr[r]), width, height, discretization, capacity_per_rank)
             f.rank, f.world = r, n
             self.fields.append(f)
-        self.mx, self.dh = self.fields[0].mx, self.fields[0].dh
+        self.mx, self.my, self.dh = self.fields[0].mx, self.fields[0].my, self.fields[0].dh
 
     def close(self):
         for f in self.fields:
@@ -193,11 +203,16 @@ class MgpuGroup:
         loc = np.asarray(loc, dtype=np.float32).reshape(-1, 2)
         last_d = np.asarray(last_d, dtype=np.float32).reshape(-1, 2)
         col = column_of(loc[:, 0], self.fields[0].discretization)
-        for r, f in enumerate(self.fields):
-            c0, c1 = f.strip()
-            m = (col >= c0) & (col < c1)
-            if r == 0:
-                m |= col >= self.mx
+        row = column_of(loc[:, 1], self.fields[0].discretization)
+        for f in self.fields:
+            c0, c1, r0, r1 = f.tile()
+            mc = (col >= c0) & (col < c1)
+            if c0 == 0:
+                mc |= col >= self.mx          # the slack column belongs to the tiles holding column 0
+            mr = (row >= r0) & (row < r1)
+            if r0 == 0:
+                mr |= row >= self.my
+            m = mc & mr
             f.set_objects(ids[m], loc[m], last_d[m])
 
     def commit(self):

@@ -195,6 +195,17 @@ int flk_dist_create(float width, float height, float discretization, uint64_t ca
 int flk_dist_create_cols(float width, float height, float discretization, uint64_t capacity, int device,
                          int rank, int world, const uint8_t id128[128], const int32_t *col_bounds, flk_field **out);
 
+/* Tiles: the ranks form a grid of tile_rows rows x (world / tile_rows) columns, rank = row * columns + column, and the
+ * cell rows are split like the cell columns (row_bounds[tile_rows+1], NULL = equal heights).  Every tile exchanges with
+ * its four edge neighbours only; birds of the diagonal neighbours travel in two hops (left/right first, then the
+ * arrivals that sit in a border row are forwarded down/up).  Needs at least 2 x 2 tiles; tile_rows = 1 is the strip
+ * decomposition.  This is the 2-D block partition of flockers_mpi's Kdtree (state.rs:33) on a regular grid. */
+int flk_dist_create_tiles(float width, float height, float discretization, uint64_t capacity, int device,
+                          int rank, int world, const uint8_t id128[128], int tile_rows, const int32_t *col_bounds,
+                          const int32_t *row_bounds, flk_field **out);
+/* global cell range [col0,col1) x [row0,row1) owned by this rank (strips: all rows) */
+int flk_dist_tile(const flk_field *f, int32_t *col0, int32_t *col1, int32_t *row0, int32_t *row1);
+
 /* Boundaries that give every strip about the same number of birds: x[i*stride] (HOST) is the x coordinate of sampled
  * bird i (stride in floats: 1 for a plain array, 2 for interleaved loc, 4 for rec4).  Host-side, no device needed. */
 int flk_balance_columns(const float *x, uint64_t n, uint64_t stride, float width, float discretization, int world,
@@ -230,6 +241,9 @@ int flk_mgpu_create(float width, float height, float discretization, uint64_t ca
                     const int *devices, flk_field **out);
 int flk_mgpu_create_cols(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
                          const int *devices, const int32_t *col_bounds, flk_field **out);
+int flk_mgpu_create_tiles(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
+                          const int *devices, int tile_rows, const int32_t *col_bounds, const int32_t *row_bounds,
+                          flk_field **out);
 int flk_mgpu_commit(flk_field **handles, int n);
 int flk_mgpu_step(flk_field **handles, int n, uint64_t step, uint64_t seed, const float *injected_r,
                   uint64_t n_injected);

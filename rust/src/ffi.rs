@@ -62,6 +62,13 @@ extern "C" {
                            rank: c_int, world: c_int, id128: *const u8, out: *mut *mut flk_field) -> c_int;
     pub fn flk_dist_create_cols(width: c_float, height: c_float, discretization: c_float, capacity: u64, device: c_int,
                                 rank: c_int, world: c_int, id128: *const u8, col_bounds: *const i32, out: *mut *mut flk_field) -> c_int;
+    pub fn flk_dist_create_tiles(width: c_float, height: c_float, discretization: c_float, capacity: u64, device: c_int,
+                                 rank: c_int, world: c_int, id128: *const u8, tile_rows: c_int, col_bounds: *const i32,
+                                 row_bounds: *const i32, out: *mut *mut flk_field) -> c_int;
+    pub fn flk_dist_tile(f: *const flk_field, col0: *mut i32, col1: *mut i32, row0: *mut i32, row1: *mut i32) -> c_int;
+    pub fn flk_mgpu_create_tiles(width: c_float, height: c_float, discretization: c_float, capacity_per_rank: u64, n: c_int,
+                                 devices: *const c_int, tile_rows: c_int, col_bounds: *const i32, row_bounds: *const i32,
+                                 out: *mut *mut flk_field) -> c_int;
     pub fn flk_balance_columns(x: *const c_float, n: u64, stride: u64, width: c_float, discretization: c_float, world: c_int,
                                col_bounds: *mut i32) -> c_int;
     pub fn flk_mgpu_create_cols(width: c_float, height: c_float, discretization: c_float, capacity_per_rank: u64, n: c_int,

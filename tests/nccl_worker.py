@@ -78,6 +78,27 @@ def main():
         print(f"[nccl x{world}] owned total {int(owned.item())}", flush=True)
         ok &= int(owned.item()) == n
     f.close()
+    # 2b. tiles (columns and rows split, two-hop diagonal exchange) when the ranks form a 2-row grid
+    if world >= 4 and world % 2 == 0:
+        ft = DistField2D(W, W, D, capacity=n, device=local, rank=rank, world=world, tile_rows=2)
+        ft.set_objects(*to_arrays(birds))
+        ft.commit()
+        st = None
+        if rank == 0:
+            st = Field2D(W, W, D, True, capacity=n, device=local)
+            st.set_objects(*to_arrays(birds))
+            st.lazy_update()
+        same = True
+        for t0 in (0, 10, 20):
+            ft.run(t0, 10)
+            got = gather(ft)
+            if rank == 0:
+                st.run(t0, 10)
+                same &= bits_equal(got, from_arrays(*st.snapshot_by_id()))
+        if rank == 0:
+            print(f"[nccl x{world}] tiles {world // 2} x 2, 200k birds, 30 ticks vs single GPU: {'ok' if same else 'MISMATCH'}", flush=True)
+            ok &= same
+        ft.close()
     # 3. the flockers_mpi model as shipped (flockers_mpi/src/main.rs:38-44: 1000 birds, 100x100, 100 steps) through the
     #    State-shaped mirror, against the single-GPU Flocker with the same placement
     from examples_b200 import Flocker, Schedule

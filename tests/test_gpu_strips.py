@@ -215,3 +215,69 @@ def test_async_owned_snapshot_equals_the_synchronous_one():
             for p in ptrs:
                 L.flk_host_free(p)
     g.close()
+
+
+# ---- tiles: columns AND rows split (flk_mgpu_create_tiles), two-hop diagonal exchange ---------------------------------
+
+def tiles(birds, W, H, n, rows, cap=None, **kw):
+    from examples_b200.distributed import MgpuGroup
+    g = MgpuGroup(W, H, D, capacity_per_rank=cap or len(birds), devices=[0] * n, tile_rows=rows, **kw)
+    g.scatter_objects(*to_arrays(birds))
+    g.commit()
+    return g
+
+
+@pytest.mark.parametrize("n,rows,W,H,count", [(4, 2, 200.0, 200.0, 4000), (6, 2, 300.0, 160.0, 5000),
+                                               (6, 3, 200.0, 240.0, 5000), (9, 3, 260.0, 260.0, 7000)])
+def test_tiles_match_single_field(n, rows, W, H, count):
+    birds = uniform_birds(count, W, H)
+    f, g = single(birds, W, H), tiles(birds, W, H, n, rows)
+    assert sum(g.num_owned()) == count
+    geo = [fld.tile() for fld in g.fields]
+    assert len(set(geo)) == n                                            # n different tiles
+    for t0 in range(0, 60, 10):
+        f.run(t0, 10)
+        g.run(t0, 10)
+        assert bits_equal(from_arrays(*g.snapshot_by_id()), from_arrays(*f.snapshot_by_id())), (n, rows, t0)
+    assert sum(g.num_owned()) == count
+    for r, fld in enumerate(g.fields):                                   # get_block_by_location on the tile grid
+        c0, c1, r0, r1 = fld.tile()
+        assert fld.owner((c0 + 0.5) * D, (r0 + 0.5) * D) == r and fld.owner((c1 - 0.5) * D, (r1 - 0.5) * D) == r
+    g.close()
+
+
+def test_tiles_match_oracle_with_injected_draws_and_seam_birds():
+    W = H = 160.0
+    n = 3000
+    birds = uniform_birds(n, W, H)
+    # birds on the seam lines, in the corners and in the slack cells (x == W, y == H)
+    birds["x"][:6] = [0.0, W, W, 0.0, 80.0, W]
+    birds["y"][:6] = [0.0, H, 0.0, H, H, 80.0]
+    g = tiles(birds, W, H, 4, 2)
+    sim = O.Sim(W, H)
+    sim.init(birds)
+    rng = np.random.default_rng(5)
+    for t in range(8):
+        r = rng.random((n, 2), dtype=np.float32)
+        sim.step(injected=r)
+        g.step(t, injected=r)
+        assert bits_equal(from_arrays(*g.snapshot_by_id()), sim.agents()), t
+    g.close()
+
+
+def test_tiles_clustered_with_uneven_boundaries():
+    from examples_b200.distributed import balanced_columns, grid_columns
+    W, H = 400.0, 300.0
+    n = 9000
+    birds = clustered_birds(n, W, H, per_cluster=900, sigma=10.0)
+    ids, loc, ld = to_arrays(birds)
+    cb = balanced_columns(loc[:, 0], W, 3)
+    rb = balanced_columns(loc[:, 1], H, 2)
+    f = single(birds, W, H)
+    g = tiles(birds, W, H, 6, 2, col_bounds=cb, row_bounds=rb)
+    assert g.fields[4].tile() == (int(cb[1]), int(cb[2]), int(rb[1]), int(rb[2]))
+    for t0 in range(0, 30, 10):
+        f.run(t0, 10)
+        g.run(t0, 10)
+        assert bits_equal(from_arrays(*g.snapshot_by_id()), from_arrays(*f.snapshot_by_id())), t0
+    g.close()
