@@ -102,6 +102,7 @@ struct flk_dist_state {
     int Px = 1, Py = 1, px = 0, py = 0;
     int down = 0, up = 0;
     std::vector<int> rbounds;          // row boundaries (Py+1)
+    cudaEvent_t ev_stepped = nullptr;  // tiles: every owned bird of this tick is stepped (main stream)
     cudaEvent_t ev_fwd = nullptr;      // my lower/upper messages are complete (own successors + forwarded arrivals)
     cudaEvent_t ev_copied_y = nullptr; // the row-direction exchange is complete
 };
@@ -120,6 +121,7 @@ void dist_free(flk_field *f) {
     if (d->ev_tick) cudaEventDestroy(d->ev_tick);
     if (d->ev_copied) cudaEventDestroy(d->ev_copied);
     if (d->ev_fwd) cudaEventDestroy(d->ev_fwd);
+    if (d->ev_stepped) cudaEventDestroy(d->ev_stepped);
     if (d->ev_copied_y) cudaEventDestroy(d->ev_copied_y);
     if (d->rank == 0 && d->group) delete[] d->group;
     delete d;
@@ -216,6 +218,7 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     cudaError_t e = cudaMalloc(&d->xbuf, nbuf * xb);
     if (e == cudaSuccess) e = cudaMemsetAsync(d->xbuf, 0, nbuf * xb, f->stream);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fwd, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_stepped, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_copied_y, cudaEventDisableTiming);
     if (e == cudaSuccess) {
         int lo_p = 0, hi_p = 0;
@@ -282,7 +285,9 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
         CUDA_TRY(cudaEventRecord(e0, f->stream));
     }
     const uint32_t dh = (uint32_t)f->g.dh, nown = (uint32_t)f->g.nown;
-    const bool split = nown >= 5 && d->overlap && f->g.mode == 1;   // tiles: border cells are not index ranges; no overlap yet
+    // tiles: the border COLUMNS are stepped first too, so the left/right exchange and its unpack run beside the interior
+    // step; the lower/upper messages are complete only when every column is done (border rows are not an index range)
+    const bool split = nown >= 5 && d->overlap;
     if (split) {
         // border: columns {ghost, 1, 2} and {nown-1, nown, ghost, slack} (ghost threads only invalidate their WRITE
         // slot), on the high-priority comm stream so that they run BESIDE the interior launch instead of ahead of it
@@ -306,6 +311,7 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
         f->launches += 1;
         CUDA_TRY(cudaEventRecord(d->ev_sent, f->stream));
     }
+    if (f->g.mode == 2) CUDA_TRY(cudaEventRecord(d->ev_stepped, f->stream));   // every owned bird of this tick is stepped
     if (prof) CUDA_TRY(cudaEventRecord(f->prof_events.back(), f->stream));
     CUDA_TRY(cudaGetLastError());
     return FLK_OK;
@@ -342,11 +348,12 @@ static int dist_phase_exchange(flk_field *f) {
 // lower/upper messages (the diagonal neighbours' birds travel in two hops, so every tile talks to four peers only)
 static int dist_phase_unpack_x(flk_field *f) {
     flk_dist_state *d = f->dist;
-    CUDA_TRY(cudaStreamWaitEvent(f->stream, d->ev_copied, 0));
-    launch_unpack(f->g, f->s, f->stream, 0);
+    cudaStream_t cs = d->comm_stream;           // behind the left/right exchange in stream order, beside the interior step
+    launch_unpack(f->g, f->s, cs, 0);
     f->launches += 1;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(d->ev_fwd, f->stream));
+    CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_stepped, 0));   // my own successors are all in the lower/upper messages
+    CUDA_TRY(cudaEventRecord(d->ev_fwd, cs));
     return FLK_OK;
 }
 

@@ -619,6 +619,7 @@ void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs 
     if (g.mode == 2) {   // rows split: every variant is the TILES instantiation (ghost rows, local row arithmetic)
         if (p.relax) {
             if (a.math_mode == 1) { if (tile) FLK_LAUNCH_T(true, 1, true); else FLK_LAUNCH_T(true, 1, false); }
+            else if (tile && fastg) k_step<true, 0, true, true, true><<<grid, block, 0, st>>>(g, p, s, a);
             else { if (tile) FLK_LAUNCH_T(true, 0, true); else FLK_LAUNCH_T(true, 0, false); }
         } else {
             if (a.math_mode == 1) FLK_LAUNCH_T(false, 1, false);
