@@ -1,5 +1,5 @@
 """Soak: 16 M birds, hundreds of ticks, single field vs 4 in-process strips on one GPU, compared bit for bit (rare
-events: x == W slack cells, seam crossings, migration bursts).  python tools/soak.py [ticks]"""
+events: x == W slack cells, seam crossings, migration bursts).  python tools/soak.py [ticks] [tile_rows]"""
 import sys, time, hashlib
 sys.path.insert(0, '.')
 import numpy as np
@@ -13,7 +13,8 @@ W, H = bench.field_size(gx), bench.field_size(gy)
 loc = bench.make_birds(n, W, H, False)
 ids = np.arange(n, dtype=np.uint32); ld = np.zeros_like(loc)
 f = Field2D(W, H, D, True, capacity=n); f.set_objects(ids, loc, ld); f.lazy_update()
-g = MgpuGroup(W, H, D, capacity_per_rank=int(n / 4 * 1.2) + 100000, devices=[0] * 4)
+tile_rows = int(sys.argv[2]) if len(sys.argv) > 2 else 1   # 2: 2 x 2 tiles instead of 4 strips
+g = MgpuGroup(W, H, D, capacity_per_rank=int(n / 4 * 1.2) + 100000, devices=[0] * 4, tile_rows=tile_rows)
 g.scatter_objects(ids, loc, ld); g.commit()
 def digest(t):
     i, l, d = t
