@@ -228,7 +228,8 @@ int flk_dist_step(flk_field *f, uint64_t step, uint64_t seed, const float *injec
 
 /* number of birds this rank owns (ghost copies excluded) — synchronising; reports capacity overflows */
 int flk_dist_num_owned(flk_field *f, uint64_t *n);
-/* flk_snapshot restricted to the birds this rank owns */
+/* flk_snapshot restricted to the birds this rank owns.  Strips: (cell, id) order.  Tiles: the owned birds are compacted
+ * out of the READ buffer in no particular order (sort by id if an order is needed). */
 int flk_dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n);
 
 /* as above, but the copies of the records are only enqueued: *n is exact on return (the call waits for the tick that
