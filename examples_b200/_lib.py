@@ -44,6 +44,8 @@ SIGNATURES = {
     "flk_set_objects_dense": [_vp, _u64, _u32, _vp],
     "flk_snapshot_dense": [_vp, _u32, _u64, _vp],
     "flk_snapshot_dense_async": [_vp, _u32, _u64, _vp],
+    "flk_frame_begin": [_vp, _vp, _vp, _P(_u64)],
+    "flk_frame_wait": [_vp],
     "flk_get_binning": [_vp, _vp, _vp],
     "flk_get_object": [_vp, _u32, _P(_f32), _P(_i32)],
     "flk_synchronize": [_vp],

@@ -73,6 +73,11 @@ void field_free(flk_field *f) {
     if (f->d_paystage) cudaFree(f->d_paystage);
     if (f->d_injected) cudaFree(f->d_injected);
     if (f->h_dense) cudaFreeHost(f->h_dense);
+    if (f->frame_rec) cudaFree(f->frame_rec);
+    if (f->frame_ids) cudaFree(f->frame_ids);
+    if (f->ev_frame_ready) cudaEventDestroy(f->ev_frame_ready);
+    if (f->ev_frame_done) cudaEventDestroy(f->ev_frame_done);
+    if (f->frame_stream) cudaStreamDestroy(f->frame_stream);
     if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
     for (auto &e : f->prof_events) cudaEventDestroy(e);
     for (auto &e : f->prof_rebin) cudaEventDestroy(e);
@@ -494,6 +499,45 @@ int flk_snapshot_dense(flk_field *f, uint32_t id0, uint64_t n, float *rec4) {
 
 int flk_snapshot_dense_async(flk_field *f, uint32_t id0, uint64_t n, float *rec4) {
     return snapshot_dense_impl(f, id0, n, rec4, false);
+}
+
+// ---- frames for a front-end: the READ buffer is copied aside on the handle's stream (device to device), then a side
+// stream moves that copy to the host while the handle's stream is free to run the next ticks
+int flk_frame_begin(flk_field *f, uint32_t *id, float *rec4, uint64_t *n) {
+    CHECK_HANDLE(f);
+    if (f->g.mode != 0) return fail(FLK_E_UNSUPPORTED, "frames are taken from single-GPU handles (use flk_dist_snapshot_owned_async on a strip)");
+    if (!f->frame_stream) {
+        CUDA_TRY(cudaMalloc(&f->frame_rec, f->cap * sizeof(Rec)));
+        CUDA_TRY(cudaMalloc(&f->frame_ids, f->cap * 4));
+        CUDA_TRY(cudaStreamCreateWithFlags(&f->frame_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&f->ev_frame_ready, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&f->ev_frame_done, cudaEventDisableTiming));
+    }
+    const uint64_t nr = f->n_read;
+    if (n) *n = nr;
+    // the previous frame may still be on its way to the host: do not overwrite the copy it is reading
+    if (f->frame_pending) CUDA_TRY(cudaStreamWaitEvent(f->stream, f->ev_frame_done, 0));
+    if (nr) {
+        if (rec4) CUDA_TRY(cudaMemcpyAsync(f->frame_rec, f->s.rec, nr * sizeof(Rec), cudaMemcpyDeviceToDevice, f->stream));
+        if (id) CUDA_TRY(cudaMemcpyAsync(f->frame_ids, f->s.ids, nr * 4, cudaMemcpyDeviceToDevice, f->stream));
+    }
+    CUDA_TRY(cudaEventRecord(f->ev_frame_ready, f->stream));
+    CUDA_TRY(cudaStreamWaitEvent(f->frame_stream, f->ev_frame_ready, 0));
+    if (nr) {
+        if (rec4) CUDA_TRY(cudaMemcpyAsync(rec4, f->frame_rec, nr * sizeof(Rec), cudaMemcpyDeviceToHost, f->frame_stream));
+        if (id) CUDA_TRY(cudaMemcpyAsync(id, f->frame_ids, nr * 4, cudaMemcpyDeviceToHost, f->frame_stream));
+    }
+    CUDA_TRY(cudaEventRecord(f->ev_frame_done, f->frame_stream));
+    f->frame_pending = true;
+    return FLK_OK;
+}
+
+int flk_frame_wait(flk_field *f) {
+    CHECK_HANDLE(f);
+    if (!f->frame_pending) return FLK_OK;
+    CUDA_TRY(cudaEventSynchronize(f->ev_frame_done));
+    f->frame_pending = false;
+    return FLK_OK;
 }
 
 int flk_get_object(flk_field *f, uint32_t id, float out[4], int32_t *found) {

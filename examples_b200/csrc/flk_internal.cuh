@@ -25,6 +25,12 @@ struct flk_field {
     uint32_t *d_paystage = nullptr;   // upload staging of payload words
     uint64_t paystage_cap = 0;
     float2 *d_injected = nullptr;
+    // flk_frame_*: a device-side copy of the READ buffer that a side stream downloads while the simulation goes on
+    flk::Rec *frame_rec = nullptr;
+    uint32_t *frame_ids = nullptr;
+    cudaStream_t frame_stream = nullptr;
+    cudaEvent_t ev_frame_ready = nullptr, ev_frame_done = nullptr;
+    bool frame_pending = false;
     uint32_t *h_dense = nullptr;      // pinned word: ids outside the range of the last dense snapshot
     bool dense_pending = false;
     uint64_t injected_cap = 0;

@@ -252,6 +252,17 @@ class Field2D:
         """enqueue only; call synchronize() before reading the (pinned) buffer"""
         check(self._L.flk_snapshot_dense_async(self._h, id0, n, C.c_void_p(ptr)))
 
+    # ---- frames for a front-end: download beside the simulation
+    def frame_begin_raw(self, id_ptr: int, rec4_ptr: int) -> int:
+        """enqueue a frame (pinned host buffers); ticks enqueued afterwards run while it downloads; -> object count"""
+        n = C.c_uint64()
+        check(self._L.flk_frame_begin(self._h, C.c_void_p(id_ptr) if id_ptr else None,
+                                      C.c_void_p(rec4_ptr) if rec4_ptr else None, C.byref(n)))
+        return n.value
+
+    def frame_wait(self):
+        check(self._L.flk_frame_wait(self._h))
+
     def snapshot_by_id(self):
         ids, loc, ld = self.snapshot()
         o = np.argsort(ids, kind="stable")

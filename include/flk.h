@@ -145,6 +145,14 @@ int flk_set_objects_dense(flk_field *f, uint64_t n, uint32_t id0, const float *r
 int flk_snapshot_dense(flk_field *f, uint32_t id0, uint64_t n, float *rec4);
 int flk_snapshot_dense_async(flk_field *f, uint32_t id0, uint64_t n, float *rec4);
 
+/* Frames for a front-end (Field2D::get / get_location for every object, once per rendered frame:
+ * flockers/src/visualization/vis_state.rs:52, bird_vis.rs:23) without stopping the simulation: flk_frame_begin copies the
+ * READ buffer aside on the device and lets a side stream move that copy to the HOST arrays (pinned; id[n], rec4[4n] =
+ * {loc.x, loc.y, last_d.x, last_d.y}, (cell, id) order; either may be NULL) while flk_run / flk_step calls made afterwards
+ * proceed; the arrays are valid after flk_frame_wait.  One frame in flight per handle (a second begin queues behind it). */
+int flk_frame_begin(flk_field *f, uint32_t *id, float *rec4, uint64_t *n);
+int flk_frame_wait(flk_field *f);
+
 /* flk_snapshot plus the payload bytes, same order */
 int flk_snapshot_ex(flk_field *f, uint32_t *id, float *loc, float *last_d, void *payload, uint64_t *n);
 

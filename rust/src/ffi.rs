@@ -42,6 +42,8 @@ extern "C" {
     pub fn flk_set_objects_dense(f: *mut flk_field, n: u64, id0: u32, rec4: *const c_float) -> c_int;
     pub fn flk_snapshot_dense(f: *mut flk_field, id0: u32, n: u64, rec4: *mut c_float) -> c_int;
     pub fn flk_snapshot_dense_async(f: *mut flk_field, id0: u32, n: u64, rec4: *mut c_float) -> c_int;
+    pub fn flk_frame_begin(f: *mut flk_field, id: *mut u32, rec4: *mut c_float, n: *mut u64) -> c_int;
+    pub fn flk_frame_wait(f: *mut flk_field) -> c_int;
     pub fn flk_get_object(f: *mut flk_field, id: u32, out: *mut c_float, found: *mut i32) -> c_int;
     pub fn flk_get_binning(f: *mut flk_field, cell_start: *mut u32, sorted_ids: *mut u32) -> c_int;
     pub fn flk_synchronize(f: *mut flk_field) -> c_int;

@@ -278,3 +278,37 @@ def test_async_snapshots_on_two_handles_overlap_safely():
             f.close()
         for p in bufs:
             L.flk_host_free(p)
+
+
+def test_frames_download_beside_the_simulation():
+    """flk_frame_begin / flk_frame_wait: the frame is the state at the time of the call even though later ticks are
+    enqueued (and overwrite the READ buffer) before the download has finished"""
+    import ctypes as C
+    from examples_b200 import _lib
+    L = _lib.load()
+    W = H = 600.0
+    n = 60000
+    birds = make(n, W, H, seed=31)
+    a, b = gpu(birds, W, H), gpu(birds, W, H)
+    a.run(0, 10); b.run(0, 10)
+    want_ids, want_loc, want_ld = b.snapshot()                 # (cell, id) order at tick 10
+    p_id, p_rec = C.c_void_p(), C.c_void_p()
+    _lib.check(L.flk_host_alloc(C.byref(p_id), 4 * n)); _lib.check(L.flk_host_alloc(C.byref(p_rec), 16 * n))
+    try:
+        for frame in range(2):                                  # the second begin queues behind the first
+            got = a.frame_begin_raw(p_id.value, p_rec.value)
+            assert got == n
+            a.run(10 + 30 * frame, 30)                          # keeps the GPU busy and rewrites the READ buffer
+            a.frame_wait()
+            ids = np.ctypeslib.as_array(C.cast(p_id, C.POINTER(C.c_uint32)), shape=(n,)).copy()
+            rec = np.ctypeslib.as_array(C.cast(p_rec, C.POINTER(C.c_float)), shape=(n, 4)).copy()
+            if frame == 0:
+                assert np.array_equal(ids, want_ids)
+                assert bits_equal(rec[:, :2].copy(), want_loc) and bits_equal(rec[:, 2:].copy(), want_ld)
+            else:
+                b.run(10, 30)
+                i2, l2, d2 = b.snapshot()
+                assert np.array_equal(ids, i2) and bits_equal(rec[:, :2].copy(), l2) and bits_equal(rec[:, 2:].copy(), d2)
+        a.synchronize()
+    finally:
+        L.flk_host_free(p_id); L.flk_host_free(p_rec)
