@@ -503,6 +503,49 @@ ORC_API int64_t orc_sim_step_strip(orc_sim *s, uint64_t step, uint64_t seed, con
     return nl;
 }
 
+/* the same for a 2-D block (tile): global cell columns [col0,col1) x rows [row0,row1); the slack column / row belong
+ * to the blocks holding column 0 / row 0 (flockers_mpi partitions the field in 2-D blocks, state.rs:33,75) */
+ORC_API int64_t orc_sim_step_tile(orc_sim *s, uint64_t step, uint64_t seed, const float *injected,
+                                  int col0, int col1, int row0, int row1, orc_bird *out_leavers, int64_t cap) {
+    orc_field *f = s->field;
+    const orc_cfg *c = &s->cfg;
+    int64_t nl = 0, kept = 0;
+    orc_vec v = {0, 0, 0};
+    for (int64_t i = 0; i < s->n; ++i) {
+        orc_bird *a = &s->agents[i];
+        float r1, r2; int drew;
+        if (injected) { r1 = injected[2 * (size_t)a->id]; r2 = injected[2 * (size_t)a->id + 1]; }
+        else orc_draw(seed, a->id, step, &r1, &r2);
+        bird_step(f, a, c, r1, r2, &v, &drew);
+        int cx, cy;
+        discretize(f, a->x, a->y, &cx, &cy);
+        int mine = ((cx >= col0 && cx < col1) || (cx >= f->mx && col0 == 0)) &&
+                   ((cy >= row0 && cy < row1) || (cy >= f->my && row0 == 0));
+        if (!mine) {
+            orc_bag *b = cell_bag(f, f->write, cx, cy);
+            b->n -= 1; /* the push just made is the last element */
+            if (nl < cap) out_leavers[nl] = *a;
+            ++nl;
+        } else {
+            s->agents[kept++] = *a;
+        }
+    }
+    free(v.v);
+    s->n = kept;
+    return nl;
+}
+
+/* birds of the READ buffer in the cell rectangle [c0,c1) x [r0,r1) (no wrap: the caller passes wrapped pieces) */
+ORC_API int64_t orc_field_cells(const orc_field *f, int c0, int c1, int r0, int r1, orc_bird *out, int64_t cap) {
+    int64_t n = 0;
+    for (int cx = c0; cx < c1; ++cx)
+        for (int cy = r0; cy < r1; ++cy) {
+            const orc_bag *b = &f->bags[f->read][(size_t)cx * (size_t)f->dh + (size_t)cy];
+            for (uint32_t e = 0; e < b->n; ++e) { if (n < cap) out[n] = b->v[e]; ++n; }
+        }
+    return n;
+}
+
 /* arrivals after migration: schedule + insert into WRITE (state.rs:167-174) */
 ORC_API void orc_sim_add_agents(orc_sim *s, const orc_bird *arr, int64_t n) {
     s->agents = (orc_bird *)realloc(s->agents, (size_t)(s->n + n > 0 ? s->n + n : 1) * sizeof(orc_bird));

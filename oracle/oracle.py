@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
             "orc_sim_step_strip": (i64, [vp, u64, u64, vp, i32, i32, vp, i64]),
             "orc_sim_add_agents": (None, [vp, vp, i64]),
             "orc_field_columns": (i64, [vp, i32, i32, vp, i64]),
+            "orc_field_cells": (i64, [vp, i32, i32, i32, i32, vp, i64]),
+            "orc_sim_step_tile": (i64, [vp, u64, u64, vp, i32, i32, i32, i32, vp, i64]),
             "orc_max_threads": (i32, []),
         }
         for name, (res, args) in sig.items():
@@ -185,6 +187,13 @@ class Field:
         lib().orc_field_columns(self.h, c0, c1, _ptr(out), n)
         return out[:n]
 
+    def cells(self, c0, c1, r0, r1) -> np.ndarray:
+        """READ birds of the cell rectangle [c0,c1) x [r0,r1)"""
+        n = lib().orc_field_cells(self.h, c0, c1, r0, r1, None, 0)
+        out = np.zeros(max(n, 1), dtype=BIRD)
+        lib().orc_field_cells(self.h, c0, c1, r0, r1, _ptr(out), n)
+        return out[:n]
+
     def bird_step(self, bird: np.ndarray, cfg: Cfg, r1, r2):
         b = np.array(bird, dtype=BIRD).reshape(())
         drew = lib().orc_bird_step(self.h, _ptr(b), C.byref(cfg), r1, r2)
@@ -236,6 +245,16 @@ class Sim:
             injected = np.ascontiguousarray(injected, dtype=np.float32)
             inj = _ptr(injected)
         nl = lib().orc_sim_step_strip(self.h, step, seed, inj, col0, col1, _ptr(out), n)
+        return out[:nl].copy()
+
+    def step_tile(self, step, seed, injected, col0, col1, row0, row1):
+        n = lib().orc_sim_num_agents(self.h)
+        out = np.zeros(max(n, 1), dtype=BIRD)
+        inj = None
+        if injected is not None:
+            injected = np.ascontiguousarray(injected, dtype=np.float32)
+            inj = _ptr(injected)
+        nl = lib().orc_sim_step_tile(self.h, step, seed, inj, col0, col1, row0, row1, _ptr(out), n)
         return out[:nl].copy()
 
     def add_agents(self, birds):

@@ -199,3 +199,107 @@ def test_tile_two_hop_routing_delivers_every_ghost_exactly_once(Px, Py, mx, my):
                     # only if the axis is so short that ghost rings overlap; the grids used here avoid that
                     assert sorted(set(got)) == sorted(got), (px, py, gx, gy, got)
                     assert set(got) == expect, (px, py, gx, gy, sorted(got), sorted(expect))
+
+
+# ---- tiles over gloo: the two-hop halo + migration protocol with the CPU oracle as the per-rank compute --------------
+
+def _exchange_pair(dist, torch, O, lo_rank, hi_rank, out_lo, out_hi):
+    """one message to the neighbour on the low side and one to the high side of an axis; returns (from_lo, from_hi).
+    With two tiles along the axis both neighbours are the same rank: the peer's first message (its low-side one) is
+    what arrives on my high side, exactly the ordering rule of the NCCL exchange."""
+    def to_t(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).copy())
+
+    sl, sh = to_t(out_lo), to_t(out_hi)
+    nl, nh = torch.tensor([sl.numel()]), torch.tensor([sh.numel()])
+    rl, rh = torch.zeros(1, dtype=torch.int64), torch.zeros(1, dtype=torch.int64)
+    for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, nl, lo_rank), dist.P2POp(dist.isend, nh, hi_rank),
+                                     dist.P2POp(dist.irecv, rh, hi_rank), dist.P2POp(dist.irecv, rl, lo_rank)]):
+        w.wait()
+    bl, bh = torch.zeros(int(rl), dtype=torch.uint8), torch.zeros(int(rh), dtype=torch.uint8)
+    for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, sl, lo_rank), dist.P2POp(dist.isend, sh, hi_rank),
+                                     dist.P2POp(dist.irecv, bh, hi_rank), dist.P2POp(dist.irecv, bl, lo_rank)]):
+        w.wait()
+    return bl.numpy().view(O.BIRD).copy(), bh.numpy().view(O.BIRD).copy()
+
+
+def _tile_worker(rank, Px, Py, port, n, W, H, ticks, q):
+    import torch
+    import torch.distributed as dist
+    from examples_b200.distributed import column_of, grid_columns
+    from oracle import oracle as O
+    world = Px * Py
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    px, py = rank % Px, rank // Px
+    mx, my = grid_columns(W, D), grid_columns(H, D)
+    c0, c1 = px * mx // Px, (px + 1) * mx // Px
+    r0, r1 = py * my // Py, (py + 1) * my // Py
+    left, right = py * Px + (px - 1) % Px, py * Px + (px + 1) % Px
+    down, up = ((py - 1) % Py) * Px + px, ((py + 1) % Py) * Px + px
+    birds = uniform_birds(n, W, H)
+    cx, cy = column_of(birds["x"], D), column_of(birds["y"], D)
+    mine = (((cx >= c0) & (cx < c1)) | ((cx >= mx) & (c0 == 0))) & (((cy >= r0) & (cy < r1)) | ((cy >= my) & (r0 == 0)))
+    sim = O.Sim(W, H)
+    sim.init(birds[mine])
+    sim.field.lazy_update()
+    F = sim.field
+    cat = lambda parts: np.concatenate(parts) if parts else np.zeros(0, dtype=O.BIRD)
+    seed = 0xB12D
+    for t in range(ticks):
+        # before_step, hop 1: my first / last owned column (owned rows) become the left / right neighbour's ghosts
+        fl, fr = _exchange_pair(dist, torch, O, left, right, F.cells(c0, c0 + 1, r0, r1), F.cells(c1 - 1, c1, r0, r1))
+        F.insert_read(fl); F.insert_read(fr)
+        # hop 2: my first / last owned row INCLUDING the ghost columns just received (the diagonal neighbours' cells)
+        gl, gr = (c0 - 1) % mx, c1 % mx
+        row = lambda r: cat([F.cells(gl, gl + 1, r, r + 1), F.cells(c0, c1, r, r + 1), F.cells(gr, gr + 1, r, r + 1)])
+        fd, fu = _exchange_pair(dist, torch, O, down, up, row(r0), row(r1 - 1))
+        F.insert_read(fd); F.insert_read(fu)
+        # every owned Bird::step; a bird that leaves the block is reported, not kept
+        leavers = sim.step_tile(t, seed, None, c0, c1, r0, r1)
+        lx, ly = column_of(leavers["x"], D), column_of(leavers["y"], D)
+        assert np.all(lx < mx) and np.all(ly < my)                 # the slack cells are reached from their own block only
+        go_l, go_r = lx == (c0 - 1) % mx, lx == c1 % mx
+        assert np.all(go_l | go_r | ((lx >= c0) & (lx < c1)))       # JUMP < d: one cell at most
+        # after_step, hop 1: along x (whatever the row), hop 2: along y, forwarding what hop 1 brought in
+        al, ar = _exchange_pair(dist, torch, O, left, right, leavers[go_l], leavers[go_r])
+        pool = cat([leavers[~go_l & ~go_r], al, ar])
+        py_ = column_of(pool["y"], D)
+        go_d, go_u = py_ == (r0 - 1) % my, py_ == r1 % my
+        ad, au = _exchange_pair(dist, torch, O, down, up, pool[go_d], pool[go_u])
+        arrivals = cat([pool[~go_d & ~go_u], ad, au])
+        acx, acy = column_of(arrivals["x"], D), column_of(arrivals["y"], D)
+        assert np.all((acx >= c0) & (acx < c1) & (acy >= r0) & (acy < r1))
+        sim.add_agents(arrivals)
+        sim.field.lazy_update()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, sim.agents().view(np.uint8).tobytes())
+    if rank == 0:
+        allb = np.concatenate([np.frombuffer(g, dtype=O.BIRD) for g in gathered])
+        q.put(np.sort(allb, order="id").view(np.uint8).tobytes())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("Px,Py", [(2, 2), (3, 2)])
+def test_tile_two_hop_protocol_matches_single_process_oracle(Px, Py):
+    """world_size 4 and 6 over gloo: 2-D blocks, ghosts and migrants of the diagonal neighbours in two hops"""
+    import torch.multiprocessing as mp
+    from oracle import oracle as O
+    O.build()
+    n, W, H, ticks = 1800, 120.0, 100.0, 20
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_tile_worker, args=(r, Px, Py, port, n, W, H, ticks, q)) for r in range(Px * Py)]
+    for p in procs:
+        p.start()
+    data = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = np.frombuffer(data, dtype=O.BIRD)
+    sim = O.Sim(W, H)
+    sim.init(uniform_birds(n, W, H))
+    for _ in range(ticks):
+        sim.step()
+    assert len(got) == n
+    assert bits_equal(got, sim.agents())
