@@ -151,10 +151,12 @@ def ncu_traffic_per_launch(birds_per_launch: int):
 # --------------------------------------------------------------------------------------------------
 
 def cpu_oracle_run(n_birds: int, ticks: int, warm: int, clustered: bool, threads: int | None = None):
+    threads = threads or (os.cpu_count() or 1)
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is entitled to all host threads, and libgomp
+    # reads the variable when the oracle library is loaded (below)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
     from oracle import oracle as O
     O.build()
-    threads = threads or (os.cpu_count() or 1)
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
     cells = max(int(round((n_birds / 0.0996) ** 0.5 / D)), 3)
     W = field_size(cells)
     loc = make_birds(n_birds, W, W, clustered)
@@ -174,6 +176,16 @@ def cpu_oracle_run(n_birds: int, ticks: int, warm: int, clustered: bool, threads
 
 def run_reference(args, world: int, rank: int):
     if rank != 0:
+        return
+    # torchrun exports OMP_NUM_THREADS=1 to every rank, and libgomp started that way runs the oracle's parallel regions
+    # several times slower even when they ask for more threads.  The reference arm is entitled to all host threads:
+    # re-run it in a child process whose environment says so from the start.
+    want = str(os.cpu_count() or 1)
+    if os.environ.get("OMP_NUM_THREADS", want) != want and not os.environ.get("FLK_REFERENCE_CHILD"):
+        env = dict(os.environ, OMP_NUM_THREADS=want, FLK_REFERENCE_CHILD="1")
+        res = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env)
+        if res.returncode != 0:
+            raise SystemExit(res.returncode)
         return
     gx, gy, n_total, label = workload_geometry(args.workload, world, args.birds_per_gpu)
     n_sample = min(n_total, args.cpu_birds)

@@ -422,6 +422,11 @@ ORC_API void orc_make_uniform(uint64_t seed, float w, float h, int64_t n, orc_bi
 /* one Schedule::step: (step==0: update) ; every agent's step ; update.
  * injected (nullable): float pairs indexed by id; else Philox(seed, id, step). */
 ORC_API void orc_sim_step(orc_sim *s, uint64_t seed, const float *injected, int threads) {
+#ifdef _OPENMP
+    /* every parallel region of the tick (the agents' loop AND lazy_update's bag sort) uses the requested thread count,
+     * whatever OMP_NUM_THREADS said when libgomp was loaded (torchrun exports OMP_NUM_THREADS=1 to its ranks) */
+    if (threads > 1) omp_set_num_threads(threads);
+#endif
     if (s->step == 0) orc_lazy_update(s->field); /* state.update(0) */
     const uint64_t step = s->step;
     orc_field *f = s->field;
