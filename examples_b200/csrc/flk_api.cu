@@ -191,6 +191,7 @@ int enqueue_step(flk_field *f, uint64_t step, int use_step_dev, uint64_t seed, c
     a.out_base = (uint32_t)f->w_count;
     a.math_mode = f->math_mode;
     a.identity = 0;
+    a.skip_bands = 0;
     const bool prof = f->profile && !f->capturing;
     if (prof) {
         cudaEvent_t e0, e1;

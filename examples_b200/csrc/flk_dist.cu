@@ -102,6 +102,7 @@ struct flk_dist_state {
     int Px = 1, Py = 1, px = 0, py = 0;
     int down = 0, up = 0;
     std::vector<int> rbounds;          // row boundaries (Py+1)
+    bool bands = false;                // tiles: this tick stepped the border row bands ahead of the interior
     cudaEvent_t ev_stepped = nullptr;  // tiles: every owned bird of this tick is stepped (main stream)
     cudaEvent_t ev_fwd = nullptr;      // my lower/upper messages are complete (own successors + forwarded arrivals)
     cudaEvent_t ev_copied_y = nullptr; // the row-direction exchange is complete
@@ -277,6 +278,7 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
     a.out_base = 0;
     a.math_mode = f->math_mode;
     a.identity = identity;
+    a.skip_bands = 0;
     const bool prof = f->profile && !identity;
     if (prof) {
         cudaEvent_t e0, e1;
@@ -301,11 +303,22 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
             launch_step(f->g, f->p, f->s, a, f->s.capx, d->comm_stream);
             f->launches += 1;
         }
+        // tiles: the two owned rows next to each row boundary (and the slack row) of the interior columns are the only
+        // other birds whose successors enter a message: step them now as well, so that the lower/upper exchange does
+        // not have to wait for the interior step either
+        d->bands = f->g.mode == 2 && f->g.rown >= 5 && !identity;
+        if (d->bands) {
+            launch_step_bands(f->g, f->p, f->s, a, 3, (int)nown - 1, d->comm_stream);
+            f->launches += 1;
+        }
         CUDA_TRY(cudaEventRecord(d->ev_sent, d->comm_stream));
         a.cell_lo = 3 * dh; a.cell_hi = (nown - 1) * dh;
+        a.skip_bands = d->bands ? 1 : 0;
         launch_step(f->g, f->p, f->s, a, read_upper_bound(f), f->stream);
+        a.skip_bands = 0;
         f->launches += 1;
     } else {
+        d->bands = false;
         a.cell_lo = 0; a.cell_hi = f->ncell;
         launch_step(f->g, f->p, f->s, a, read_upper_bound(f), f->stream);
         f->launches += 1;
@@ -352,7 +365,8 @@ static int dist_phase_unpack_x(flk_field *f) {
     launch_unpack(f->g, f->s, cs, 0);
     f->launches += 1;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_stepped, 0));   // my own successors are all in the lower/upper messages
+    // my own successors must all be in the lower/upper messages: with the border bands stepped first they already are
+    if (!d->bands) CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_stepped, 0));
     CUDA_TRY(cudaEventRecord(d->ev_fwd, cs));
     return FLK_OK;
 }

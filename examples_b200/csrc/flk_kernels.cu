@@ -567,6 +567,7 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
             }
             mbar_wait(&bar, 0);
             if (!valid) return;
+            if (TILES && a.skip_bands && (lr <= 2 || lr >= g.rown - 1)) return;   // stepped by k_step_bands
             float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
             if (MATH == 0 && FLK_PACKED) {
                 const f32x2 ME = pk(mex, mey);
@@ -602,8 +603,38 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
             s.tkey[w] = KEY_INVALID;
             return;
         }
+        if (TILES && a.skip_bands && (lr <= 2 || lr >= g.rown - 1)) return;   // stepped by k_step_bands (slack row too)
     }
     step_bird_general<RELAX, MATH, TILES>(g, p, s, a, i, w);   // also the identity pass (re-stage unchanged)
+}
+
+// k_step_bands (tiles): one warp per (column, band); band 0 = local rows {1,2}, band 1 = rows {rown-1, rown}, band 2 = the slack row.  The birds
+// of a band are a contiguous index range of the READ buffer; each is finished by step_bird_general (a few thousand
+// birds per tick: the point is that they are done EARLY, so that the lower/upper exchange can run beside the
+// interior step)
+template <bool RELAX, int MATH>
+__global__ void __launch_bounds__(32) k_step_bands(const __grid_constant__ Geom g, const __grid_constant__ Params p,
+                                                   const __grid_constant__ Store s, const __grid_constant__ StepArgs a,
+                                                   int col_lo) {
+    const uint32_t col = (uint32_t)col_lo + blockIdx.y, dh = (uint32_t)g.dh;
+    // band 2 = the slack row (a bird at y == H steps into row my-1 or row 0, i.e. into a border row of some tile)
+    const uint32_t r_lo = blockIdx.x == 0 ? 1u : (blockIdx.x == 1 ? (uint32_t)g.rown - 1u : (uint32_t)g.rown + 2u);
+    const uint32_t r_hi = blockIdx.x == 2 ? r_lo + 1u : r_lo + 2u;
+    const uint32_t lo = s.cell_start[col * dh + r_lo], hi = s.cell_start[col * dh + r_hi];
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += 32) step_bird_general<RELAX, MATH, true>(g, p, s, a, i, a.out_base + i);
+}
+
+void launch_step_bands(const Geom &g, const Params &p, const Store &s, const StepArgs &a, int col_lo, int col_hi,
+                       cudaStream_t st) {
+    if (col_hi <= col_lo) return;
+    const dim3 grid(3, (unsigned)(col_hi - col_lo));
+    if (p.relax) {
+        if (a.math_mode == 1) k_step_bands<true, 1><<<grid, 32, 0, st>>>(g, p, s, a, col_lo);
+        else k_step_bands<true, 0><<<grid, 32, 0, st>>>(g, p, s, a, col_lo);
+    } else {
+        if (a.math_mode == 1) k_step_bands<false, 1><<<grid, 32, 0, st>>>(g, p, s, a, col_lo);
+        else k_step_bands<false, 0><<<grid, 32, 0, st>>>(g, p, s, a, col_lo);
+    }
 }
 
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,

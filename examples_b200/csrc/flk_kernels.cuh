@@ -57,6 +57,7 @@ struct StepArgs {
     uint32_t out_base;          // WRITE index of READ index 0
     int math_mode;              // 0 exact, 1 fast
     int identity;               // 1 = re-stage every owned bird unchanged (dist commit: builds the first halo)
+    int skip_bands;             // tiles: the two owned rows next to each row boundary are stepped by k_step_bands, skip them
 };
 
 void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id, const float2 *loc,
@@ -73,6 +74,10 @@ void launch_compact_owned(const Geom &g, const Store &s, uint32_t n_upper, uint3
                           uint32_t *counter, cudaStream_t st);
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st);
+// tiles: Bird::step for the two owned rows next to each row boundary of local columns [col_lo, col_hi) — the only
+// interior-column birds whose successors can enter the lower/upper messages
+void launch_step_bands(const Geom &g, const Params &p, const Store &s, const StepArgs &a, int col_lo, int col_hi,
+                       cudaStream_t st);
 // exclusive scan of cnt -> cell_start, zeroing cnt; 3 launches
 void launch_scan(const Store &s, uint32_t ncell_plus1, cudaStream_t st);
 void launch_scatter(const Store &s, uint32_t n_write_extent, int dist, cudaStream_t st);
