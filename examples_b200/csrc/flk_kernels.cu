@@ -919,32 +919,39 @@ __global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n, uint
 
 // four consecutive stepped/uploaded slots per thread: three 16-byte loads, then four independent gather -> store
 // chains in flight (the one-slot-per-thread form reached 42 % of DRAM bandwidth: too few bytes in flight per thread)
+#ifndef FLK_SCATTER_E
+#define FLK_SCATTER_E 4   // WRITE slots per thread (multiple of 4)
+#endif
 __global__ void __launch_bounds__(256) k_scatter4(const Store s, uint32_t n_limit, int use_dev_count) {
+    constexpr int E = FLK_SCATTER_E;
     const uint32_t n = use_dev_count ? min(*s.n_read_dev, n_limit) : n_limit;
-    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * (uint32_t)E;
     if (i0 >= n) return;
-    uint32_t key[4], slot[4], id[4];
-    if (i0 + 4 <= n) {
-        const uint4 k4 = *reinterpret_cast<const uint4 *>(s.tkey + i0);
-        const uint4 s4 = *reinterpret_cast<const uint4 *>(s.tslot + i0);
-        const uint4 d4 = *reinterpret_cast<const uint4 *>(s.tid + i0);
-        key[0] = k4.x; key[1] = k4.y; key[2] = k4.z; key[3] = k4.w;
-        slot[0] = s4.x; slot[1] = s4.y; slot[2] = s4.z; slot[3] = s4.w;
-        id[0] = d4.x; id[1] = d4.y; id[2] = d4.z; id[3] = d4.w;
+    uint32_t key[E], slot[E], id[E];
+    if (i0 + E <= n) {
+#pragma unroll
+        for (int q = 0; q < E / 4; ++q) {
+            const uint4 k4 = *reinterpret_cast<const uint4 *>(s.tkey + i0 + 4 * q);
+            const uint4 s4 = *reinterpret_cast<const uint4 *>(s.tslot + i0 + 4 * q);
+            const uint4 d4 = *reinterpret_cast<const uint4 *>(s.tid + i0 + 4 * q);
+            key[4 * q] = k4.x; key[4 * q + 1] = k4.y; key[4 * q + 2] = k4.z; key[4 * q + 3] = k4.w;
+            slot[4 * q] = s4.x; slot[4 * q + 1] = s4.y; slot[4 * q + 2] = s4.z; slot[4 * q + 3] = s4.w;
+            id[4 * q] = d4.x; id[4 * q + 1] = d4.y; id[4 * q + 2] = d4.z; id[4 * q + 3] = d4.w;
+        }
     } else {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
+        for (int t = 0; t < E; ++t) {
             const bool ok = i0 + t < n;
             key[t] = ok ? s.tkey[i0 + t] : KEY_INVALID;
             slot[t] = ok ? s.tslot[i0 + t] : 0u;
             id[t] = ok ? s.tid[i0 + t] : 0u;
         }
     }
-    uint32_t base[4];
+    uint32_t base[E];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) base[t] = key[t] != KEY_INVALID ? __ldg(s.cell_start + key[t]) : 0u;
+    for (int t = 0; t < E; ++t) base[t] = key[t] != KEY_INVALID ? __ldg(s.cell_start + key[t]) : 0u;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < E; ++t) {
         if (key[t] == KEY_INVALID) continue;
         const uint32_t p = base[t] + slot[t];
         if (p >= s.cap) {
@@ -959,17 +966,20 @@ void launch_scatter(const Store &s, uint32_t n, int dist, cudaStream_t st) {
     if (dist) {
         // stepped slots [0, n) (n = host upper bound of the READ population), then the two receive regions
         const uint32_t nn = n < s.cap ? n : s.cap;
-        if (nn) k_scatter4<<<((nn + 3) / 4 + 255) / 256, 256, 0, st>>>(s, nn, 1);
+        if (nn) k_scatter4<<<((nn + FLK_SCATTER_E - 1) / FLK_SCATTER_E + 255) / 256, 256, 0, st>>>(s, nn, 1);
         k_scatter<true><<<(s.nrecv * s.capx + 255) / 256, 256, 0, st>>>(s, s.nrecv * s.capx, s.cap);
         return;
     }
     if (n == 0) return;
-    k_scatter4<<<((n + 3) / 4 + 255) / 256, 256, 0, st>>>(s, n, 0);
+    k_scatter4<<<((n + FLK_SCATTER_E - 1) / FLK_SCATTER_E + 255) / 256, 256, 0, st>>>(s, n, 0);
 }
 
 // two staged entries per thread: both record gathers and both cell-range loads are in flight before either member
 // loop starts (the one-entry form ran at 61 % of DRAM bandwidth)
-__global__ void __launch_bounds__(256) k_rank(const Store s, uint32_t ncell, int bump_step) {
+#ifndef FLK_RANK_MINBLOCKS
+#define FLK_RANK_MINBLOCKS 8   // 32 registers, full occupancy: 0.138 ms against 0.148 (6 CTAs/SM) and 0.158 (4-5)
+#endif
+__global__ void __launch_bounds__(256, FLK_RANK_MINBLOCKS) k_rank(const Store s, uint32_t ncell, int bump_step) {
     const uint32_t n = min(s.cell_start[ncell], s.cap);
     const uint32_t p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2u;
     if (p0 == 0) {
