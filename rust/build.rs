@@ -21,6 +21,8 @@ fn main() {
     assert!(status.success(), "nvcc failed");
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=flk");
+    // the library stays in OUT_DIR: give binaries and examples of this crate an rpath to it
+    println!("cargo:rustc-link-arg=-Wl,-rpath,{}", out.display());
     for f in ["flk_kernels.cu", "flk_api.cu", "flk_dist.cu", "flk_device.cuh", "flk_kernels.cuh", "flk_internal.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }

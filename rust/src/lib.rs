@@ -100,15 +100,20 @@ pub trait HasGpuField<O: FlockObject> {
 }
 
 /// The one agent scheduled instead of N birds (idiom of schelling/src/model/updater.rs, forestfire/src/model/spread.rs).
-#[derive(Clone)]
 pub struct FlockStepper<S, O> {
     pub seed: u64,
     calls: Cell<u64>,
-    _s: std::marker::PhantomData<(S, O)>,
+    _s: std::marker::PhantomData<fn() -> (S, O)>,
 }
 
 impl<S, O> FlockStepper<S, O> {
     pub fn new(seed: u64) -> Self { FlockStepper { seed, calls: Cell::new(0), _s: std::marker::PhantomData } }
+}
+
+// krabmaga boxes agents as `Box<dyn Agent>` and clones them (Agent: DynClone); written by hand so that the state and
+// object types need not be Clone themselves (a derive would ask for `S: Clone, O: Clone`)
+impl<S, O> Clone for FlockStepper<S, O> {
+    fn clone(&self) -> Self { FlockStepper { seed: self.seed, calls: self.calls.clone(), _s: std::marker::PhantomData } }
 }
 
 impl<S: State + HasGpuField<O> + 'static, O: FlockObject + 'static> Agent for FlockStepper<S, O> {
