@@ -242,12 +242,14 @@ int flk_field_create_ex(float width, float height, float discretization, int tor
     f->cap = capacity;
     f->ncell = (uint32_t)f->g.ncols * (uint32_t)f->g.dh;
     f->s.pw = payload_bytes / 4;
-    CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&f->ev0));
-    CUDA_TRY(cudaEventCreate(&f->ev1));
-    rc = field_alloc(f);
-    if (rc) { field_free(f); delete f; return rc; }
+    rc = [&]() -> int {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&f->ev0));
+        CUDA_TRY(cudaEventCreate(&f->ev1));
+        return field_alloc(f);
+    }();
+    if (rc) { field_free(f); delete f; return rc; }   // whatever was created so far (cudaFree(nullptr) is a no-op)
     *out = f;
     return FLK_OK;
 }
@@ -398,10 +400,11 @@ int flk_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed) 
             cudaError_t ce = cudaStreamEndCapture(f->stream, &graph);
             f->graph_launches = f->launches - launches_before;
             f->launches = launches_before;
-            if (rc) return rc;
+            if (rc) { if (ce == cudaSuccess) cudaGraphDestroy(graph); return rc; }
             CUDA_TRY(ce);
-            CUDA_TRY(cudaGraphInstantiate(&f->graph_exec, graph, 0));
+            ce = cudaGraphInstantiate(&f->graph_exec, graph, 0);
             cudaGraphDestroy(graph);
+            CUDA_TRY(ce);
             f->graph_valid = true; f->graph_n = f->n_read; f->graph_seed = seed;
         }
         CUDA_TRY(cudaMemcpyAsync(f->s.step_dev, &first_step, 8, cudaMemcpyHostToDevice, f->stream));

@@ -198,11 +198,13 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     uint64_t capx = 8 * (capacity / (uint64_t)narrowest) + 4096;
     if (capx > capacity) capx = capacity;
     f->s.capx = (uint32_t)capx;
-    CUDA_TRY(cudaSetDevice(device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&f->ev0));
-    CUDA_TRY(cudaEventCreate(&f->ev1));
-    rc = field_alloc(f);
+    rc = [&]() -> int {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&f->ev0));
+        CUDA_TRY(cudaEventCreate(&f->ev1));
+        return field_alloc(f);
+    }();
     if (rc) { field_free(f); delete f; return rc; }
     flk_dist_state *d = new flk_dist_state();
     f->dist = d;
