@@ -249,7 +249,10 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int TILE_CAP = 256;   // records staged per window column (4 KB); 3 columns = 12 KB per CTA
+#ifndef FLK_STEP_BS
+#define FLK_STEP_BS 128   // birds (threads) per k_step CTA
+#endif
+constexpr int TILE_CAP = 2 * FLK_STEP_BS;   // records staged per window column (4 KB); 3 columns = 12 KB per CTA
 
 // everything of Bird::step after the neighbour loop (bird.rs:73-145) + set_object_location
 template <int MATH, bool NOPAY = false, int ROWS = -1>
@@ -489,7 +492,7 @@ __device__ __noinline__ void step_bird_general(const Geom &g, const Params &p, c
 #endif
 // TILES = the rows are split too (mode 2): the row of the local cell arrays differs from the global row
 template <bool RELAX, int MATH, bool TILE, bool FASTG, bool TILES = false>
-__global__ void __launch_bounds__(128, FLK_STEP_MINBLOCKS)
+__global__ void __launch_bounds__(FLK_STEP_BS, FLK_STEP_MINBLOCKS)
 k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const __grid_constant__ Store s,
        const __grid_constant__ StepArgs a) {
     __shared__ __align__(128) float4 tile_s[TILE ? 3 * TILE_CAP + 1 : 1];
@@ -641,7 +644,7 @@ void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs 
                  cudaStream_t st) {
     if (n_upper == 0) return;
     static const int tile = [] { const char *e = getenv("FLK_STEP_TILE"); return e ? atoi(e) : 1; }();
-    const int bs = 128;
+    const int bs = FLK_STEP_BS;
     const dim3 block(bs), grid((n_upper + bs - 1) / bs);
     const bool fastg = p.relax && g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && g.d >= 0x1p-20f && g.d <= 4096.0f &&
                        s.pw == 0 && !a.identity;
