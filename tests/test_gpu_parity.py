@@ -208,6 +208,31 @@ def test_step_bit_exact_with_injected_draws(maker, n, W, relax):
         assert bits_equal(gpu_state(f), sim.agents()), f"tick {t}"
 
 
+@pytest.mark.parametrize("relax", [True, False])
+def test_step_on_a_non_toroidal_field_matches_oracle(relax):
+    """Field2D::new(w, h, d, false): the query window is clamped at the field edge while Bird::step keeps calling
+    toroidal_distance / toroidal_transform (bird.rs:54-55,137-138 do so whatever the field is) — birds on the rim."""
+    from examples_b200 import Field2D
+    W, n = 100.0, 1200
+    birds = uniform_birds(n, W, W)
+    birds["x"][:150] = np.float32(0.25)      # a column of birds on the left rim, some on the right and upper rims
+    birds["x"][150:300] = np.float32(99.75)
+    birds["y"][300:400] = np.float32(99.9)
+    f = Field2D(W, W, D, False, capacity=n)
+    f.set_params(relax=relax)
+    f.set_objects(*to_arrays(birds))
+    f.lazy_update()
+    sim = O.Sim(W, W, toroidal=False, cfg=O.default_cfg(relax=int(relax)))
+    sim.init(birds)
+    rng = np.random.default_rng(5)
+    for t in range(6):
+        r = rng.random((n, 2), dtype=np.float32)
+        sim.step(injected=r)
+        f.step(t, injected=r)
+        f.lazy_update()
+        assert bits_equal(gpu_state(f), sim.agents()), f"tick {t}"
+
+
 def test_trajectory_shipped_config_matches_golden():
     """BASELINE config 1 (1000 birds, 100x100, 200 ticks, Philox draws): every pinned tick bit-exact."""
     g = np.load(os.path.join(GOLDEN, "flockers_1000.npz"))
@@ -314,8 +339,9 @@ def test_division_helper_is_ieee():
 
 # ---- full-size properties (BASELINE sizes; the oracle is only sampled) ---------------------------------
 
-@pytest.mark.parametrize("n,W", [(1_000_000, 3200.0)])
-def test_full_size_properties(n, W):
+@pytest.mark.parametrize("n,W,ticks", [(1_000_000, 3200.0, 3), (16_000_000, 12800.0, 2)])
+def test_full_size_properties(n, W, ticks):
+    """BASELINE configs 2 and 3 (1 M birds on 480 x 480 cells, 16 M birds on 1920 x 1920 cells)"""
     birds = uniform_birds(n, W, W)
     f = load_gpu(birds, W, W)
     cs, ids = f.binning()
@@ -329,12 +355,12 @@ def test_full_size_properties(n, W):
     same = np.diff(key) == 0
     assert np.all(np.diff(ids_s.astype(np.int64))[same] > 0)                        # ascending id inside a cell
     assert np.array_equal(np.bincount(key, minlength=f.dw * f.dh), np.diff(cs.astype(np.int64)))
-    # 3 ticks on the GPU vs the threaded oracle, whole population, bit for bit
+    # a few ticks on the GPU vs the threaded oracle, whole population, bit for bit
     sim = O.Sim(W, W)
     sim.init(birds)
-    for _ in range(3):
+    for _ in range(ticks):
         sim.step(threads=O.max_threads())
-    f.run(0, 3)
+    f.run(0, ticks)
     g = gpu_state(f)
     assert bits_equal(g, sim.agents())
     # every displacement has length JUMP (bird.rs:129-133) and positions stay on the torus
