@@ -762,6 +762,7 @@ namespace flk {
 
 int upload_injected(flk_field *f, const float *r, uint64_t n) {
     if (n == 0) return FLK_OK;
+    if (n > 0xffffffffull) return fail(FLK_E_INVALID, "n_injected exceeds the u32 id space");
     if (n > f->injected_cap) {
         if (f->d_injected) { CUDA_TRY(cudaStreamSynchronize(f->stream)); cudaFree(f->d_injected); f->d_injected = nullptr; }
         CUDA_TRY(cudaMalloc(&f->d_injected, n * 8));
