@@ -132,18 +132,31 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_launch(birds_per_launch: int):
-    """DRAM bytes of one k_step launch from the committed ncu --set full capture (profiles/), or None when the
-    capture was taken on a different launch size."""
+def ncu_traffic_per_launch(birds_per_launch: int, key: str = "bytes_per_launch"):
+    """DRAM bytes (or, with key="warp_instructions_per_launch", warp-instructions) of one k_step launch from the
+    committed ncu --set full capture (profiles/), or None when the capture was taken on a different launch size."""
     p = os.path.join(ROOT, "profiles", "k_step_traffic.json")
     if os.path.exists(p):
         try:
             d = json.load(open(p))
             if int(d["birds_per_launch"]) == int(birds_per_launch):
-                return float(d["bytes_per_launch"])
+                return float(d[key])
         except Exception:
             return None
     return None
+
+
+def issue_roofline(warp_instr, kernel_ms: float, sm_count: int, sm_mhz):
+    """What actually bounds k_step (DESIGN.md roofline): warp-instructions issued per second against the issue peak of
+    the device, 4 schedulers per SM x 1 instruction per cycle at the SM clock sampled during the timed region."""
+    if not warp_instr or not sm_mhz:
+        return None
+    achieved = warp_instr / (kernel_ms * 1e-3) / 1e9
+    peak = sm_count * 4 * sm_mhz * 1e6 / 1e9
+    return {"achieved": achieved, "peak": peak, "unit": "G warp-instructions/s", "frac": achieved / peak,
+            "warp_instructions_per_launch": warp_instr,
+            "what": "ncu smsp__inst_executed.sum per k_step launch (committed capture) / live launch duration; "
+                    "peak = SMs x 4 schedulers x sampled SM clock"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -312,6 +325,8 @@ def run_ours(args, world: int, rank: int, local_rank: int):
     peak, peak_src = measured_peak_gbs()
     achieved = ALGO_BYTES_PER_UPDATE * n_local / (k_avg_ms * 1e-3) / 1e9
     traffic = ncu_traffic_per_launch(n_total // world)
+    warp_instr = ncu_traffic_per_launch(n_total // world, "warp_instructions_per_launch")
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
 
     # ---- e2e: per step, host -> device copy of every agent, one tick, device -> host read of the new state ----
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
@@ -451,7 +466,8 @@ def run_ours(args, world: int, rank: int, local_rank: int):
                          "kernel_share_of_step": k_avg_ms / (ms / args.steps), "peak_source": peak_src,
                          "other_kernels_ms": {"k_scan_x3": rebin_ms[0], "k_scatter": rebin_ms[1], "k_rank": rebin_ms[2]},
                          "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
-                         "note": "path is FP32-issue bound, not HBM bound (DESIGN.md roofline)"},
+                         "issue_slots": issue_roofline(warp_instr, k_avg_ms, sm_count, (clocks or {}).get("sm_mhz")),
+                         "note": "path is FP32-issue bound, not HBM bound (DESIGN.md roofline): see issue_slots"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "bird-updates/s", "h2d_bytes_per_step": e2e_bytes,
                     "d2h_bytes_per_step": e2e_bytes, "steps": e2e_steps, **e2e_extra},
