@@ -7,6 +7,8 @@
 //!   Bird::step for every bird                     flockers/src/model/bird.rs:27-145  -> `step_all`
 //! The reference methods return no `Result`; a non-zero libflk code panics with `flk_last_error()`.
 pub mod ffi;
+#[cfg(feature = "distributed")]
+pub mod dist;
 
 use krabmaga::engine::agent::Agent;
 use krabmaga::engine::location::Real2D;
@@ -22,7 +24,7 @@ pub trait FlockObject: Copy {
     fn from_parts(id: u32, loc: Real2D, last_d: Real2D) -> Self;
 }
 
-fn check(rc: i32) {
+pub(crate) fn check(rc: i32) {
     if rc != ffi::FLK_OK {
         let msg = unsafe { CStr::from_ptr(ffi::flk_last_error()) }.to_string_lossy().into_owned();
         panic!("libflk error {rc}: {msg}");
