@@ -43,3 +43,15 @@ def test_reference_arm_prints_one_json_line():
     line = json.loads(res.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "bird-updates/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_roofline_inputs_come_from_the_committed_capture():
+    """roofline.traffic and roofline.issue_slots use the per-launch DRAM bytes / warp-instructions of the committed ncu
+    capture, only for the launch size it was taken on"""
+    assert bench.ncu_traffic_per_launch(16_000_000) > 16_000_000 * bench.ALGO_BYTES_PER_UPDATE
+    assert bench.ncu_traffic_per_launch(1_000_000) is None
+    wi = bench.ncu_traffic_per_launch(16_000_000, "warp_instructions_per_launch")
+    assert 16_000_000 / 32 * 500 < wi < 16_000_000 / 32 * 5000          # ~1440 instructions per warp of 32 birds
+    r = bench.issue_roofline(wi, 0.85, 148, 1965.0)
+    assert abs(r["peak"] - 148 * 4 * 1.965) < 1e-6 and 0.5 < r["frac"] < 1.0
+    assert bench.issue_roofline(None, 0.85, 148, 1965.0) is None and bench.issue_roofline(wi, 0.85, 148, None) is None
