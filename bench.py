@@ -82,44 +82,92 @@ def make_birds(n: int, W: float, H: float, clustered: bool, x0: float = 0.0, x1:
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + clock-event reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from
+    a thread every ~1 ms (a 20-tick timed region lasts ~20 ms: `nvidia-smi -lms 100` saw two samples of it); nvidia-smi
+    is the fallback when the NVML binding is missing."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         self.index, self.samples, self.proc = index, [], None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        self.sm_max = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber devices: resolve through the PCI bus id of the CUDA device
+            try:
+                import torch
+                bus = torch.cuda.get_device_properties(index).pci_bus_id  # torch >= 2.x
+                dom = getattr(torch.cuda.get_device_properties(index), "pci_domain_id", 0)
+                dev = torch.cuda.get_device_properties(index).pci_device_id
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml, self._h = pynvml, h
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
 
     def start(self):
+        if self._nvml is not None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self._nvml, self._h
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        while not self._stop.is_set():
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((mhz, [name for bit, name in bits if r & bit]))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append([p.strip() for p in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+            p = [q.strip() for q in line.split(",")]
             try:
-                sm.append(float(s[0])); mx.append(float(s[1]))
+                self.samples.append((float(p[0]), [n for n, v in zip(self.NAMES, p[2:6]) if v.lower().startswith("active")]))
+                self.sm_max = max(self.sm_max or 0.0, float(p[1]))
             except Exception:
                 continue
-            for nme, v in zip(names, s[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            self._thread = None
+            src = "nvml, 1 ms polling"
+        elif self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            src = "nvidia-smi -lms 20"
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        sm = [m for m, _ in self.samples]
+        reasons = sorted({r for _, rs in self.samples for r in rs})
+        self.samples = []
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(sm), "source": src}
 
 
 def measured_peak_gbs():
@@ -163,20 +211,42 @@ def issue_roofline(warp_instr, kernel_ms: float, sm_count: int, sm_mhz):
 # reference arm / cpu_baseline: the oracle (a port of the reference algorithm) on the host cores
 # --------------------------------------------------------------------------------------------------
 
-def cpu_oracle_run(n_birds: int, ticks: int, warm: int, clustered: bool, threads: int | None = None):
+CPU_BIRDS_CAP = 32_000_000   # largest population the CPU arm steps per tick (128 M birds x 25 ticks would take > 2 min)
+
+
+def cpu_sample_geometry(name: str, world: int, birds_per_gpu, cap: int):
+    """The CPU arm runs the workload its `config` names whenever that fits the bound (16 M birds at N=1, 32 M at N=2);
+    beyond it, the largest slice of the same workload that does: the configuration of fewer GPUs of the same weak-scaling
+    series (same rows, same density, fewer column strips).  -> (gx, gy, n, whole: bool)"""
+    gx, gy, n, _ = workload_geometry(name, world, birds_per_gpu)
+    if n <= cap:
+        return gx, gy, n, True
+    w = world
+    while w > 1:
+        w //= 2
+        gx2, gy2, n2, _ = workload_geometry(name, w, birds_per_gpu)
+        if n2 <= cap and n2 < n:
+            return gx2, gy2, n2, False
+    # a single-GPU configuration above the bound: shrink both axes, keep the density
+    scale = (cap / n) ** 0.5
+    return max(int(gx * scale), 3), max(int(gy * scale), 3), cap, False
+
+
+def cpu_oracle_run(gx: int, gy: int, n_birds: int, ticks: int, warm: int, clustered: bool, threads: int | None = None):
+    """The reference algorithm (oracle port) on the host cores: `n_birds` on gx x gy cells, `warm` + `ticks` ticks."""
     threads = threads or (os.cpu_count() or 1)
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is entitled to all host threads, and libgomp
     # reads the variable when the oracle library is loaded (below)
     os.environ["OMP_NUM_THREADS"] = str(threads)
     from oracle import oracle as O
     O.build()
-    cells = max(int(round((n_birds / 0.0996) ** 0.5 / D)), 3)
-    W = field_size(cells)
-    loc = make_birds(n_birds, W, W, clustered)
+    W, H = field_size(gx), field_size(gy)
+    loc = make_birds(n_birds, W, H, clustered)
     b = np.zeros(n_birds, dtype=O.BIRD)
     b["id"] = np.arange(n_birds, dtype=np.uint32)
     b["x"], b["y"] = loc[:, 0], loc[:, 1]
-    sim = O.Sim(W, W)
+    del loc
+    sim = O.Sim(W, H)
     sim.init(b)
     for _ in range(warm):
         sim.step(seed=STEP_SEED, threads=threads)
@@ -184,7 +254,17 @@ def cpu_oracle_run(n_birds: int, ticks: int, warm: int, clustered: bool, threads
     for _ in range(ticks):
         sim.step(seed=STEP_SEED, threads=threads)
     dt = time.perf_counter() - t0
-    return n_birds * ticks / dt, dt, threads, f"{n_birds} birds on {cells}x{cells} cells, {ticks} ticks (+{warm} warm-up), OpenMP over agents"
+    return n_birds * ticks / dt, dt, threads, (f"{n_birds} birds on {gx}x{gy} cells, {ticks} ticks (+{warm} warm-up), "
+                                                f"OpenMP over agents, {threads} threads")
+
+
+def common_config(args, world: int):
+    """the `config` object both arms print: it names the workload and nothing that depends on the implementation"""
+    gx, gy, n_total, label = workload_geometry(args.workload, world, args.birds_per_gpu)
+    return {"workload": label, "birds_total": n_total, "birds_per_gpu": n_total // world,
+            "cells": f"{gx}x{gy}", "data": "synthetic", "seeds": {"init": INIT_SEED, "step": STEP_SEED},
+            "l2": "inputs larger than L2 (>=20 B/bird x birds per GPU vs 126 MB)" if n_total // world >= 8_000_000
+                  else "working set fits L2 (reference config size)"}
 
 
 def run_reference(args, world: int, rank: int):
@@ -200,14 +280,16 @@ def run_reference(args, world: int, rank: int):
         if res.returncode != 0:
             raise SystemExit(res.returncode)
         return
-    gx, gy, n_total, label = workload_geometry(args.workload, world, args.birds_per_gpu)
-    n_sample = min(n_total, args.cpu_birds)
-    value, dt, threads, sample = cpu_oracle_run(n_sample, args.steps, args.warmup, args.workload == "clustered")
+    gx, gy, n, whole = cpu_sample_geometry(args.workload, world, args.birds_per_gpu, args.cpu_birds)
+    value, dt, threads, sample = cpu_oracle_run(gx, gy, n, args.steps, args.warmup, args.workload == "clustered")
+    sample = ("the whole workload: " if whole else "bounded sample of the workload: ") + sample
     line = {
         "impl": "reference", "metric": "bird-updates/sec", "value": value, "unit": "bird-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": label, "note": "reference algorithm on host cores, bounded sample of the workload"},
+        "higher_is_better": True, "scaling": "strong" if args.workload == "strong16m" else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": common_config(args, world),
+        "sample_is_whole_workload": whole,
         "cpu_baseline": {"value": value, "unit": "bird-updates/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "bird-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -229,99 +311,102 @@ def run_ours(args, world: int, rank: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from examples_b200 import distributed as fdist
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce_over_ranks(x: float, op) -> float:
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
+
+    def max_over_ranks(x: float) -> float:
+        return reduce_over_ranks(x, dist.ReduceOp.MAX if world > 1 else None)
 
     def sum_over_ranks(x: float) -> float:
+        return reduce_over_ranks(x, dist.ReduceOp.SUM if world > 1 else None)
+
+    def build_field(workload: str, birds_per_gpu):
+        """this rank's field (or strip) of `workload` with its birds uploaded and published"""
+        gx, gy, n_total, label = workload_geometry(workload, world, birds_per_gpu)
+        W, H = field_size(gx), field_size(gy)
+        clustered = workload == "clustered"
+        n_local = n_total // world
+        cap = int(n_local * 1.25) + 65536
         if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    gx, gy, n_total, label = workload_geometry(args.workload, world, args.birds_per_gpu)
-    W, H = field_size(gx), field_size(gy)
-    clustered = args.workload == "clustered"
-    n_local = n_total // world
-    cap = int(n_local * 1.25) + 65536
-
-    # ---- build this rank's field and its birds (each rank generates the birds of its own strip) ----
-    if world == 1:
-        f = Field2D(W, H, D, True, capacity=cap, device=local_rank)
-        loc = make_birds(n_local, W, H, clustered)
-        id_base = 0
-    else:
-        from examples_b200 import distributed as fdist
-        f = fdist.DistField2D(W, H, D, capacity=cap, device=local_rank, rank=rank, world=world, tile_rows=args.tile_rows)
-        c0, c1, r0, r1 = f.tile()
-        x0 = float(np.float32(c0) * np.float32(D))
-        x1 = float(np.float32(c1) * np.float32(D)) if c1 < gx else W
-        loc = make_birds(n_local, W, H, clustered, x0, x1, seed=INIT_SEED + rank)
-        # f32 rounding at the strip edges: keep every generated bird inside the columns this rank owns
-        col = fdist.column_of(loc[:, 0], D)
-        off = (col < c0) | (col >= c1)
-        loc[off, 0] = np.float32(0.5 * (x0 + x1))
-        if args.tile_rows > 1:   # tiles: squeeze the y coordinates into the rows this rank owns
-            y0 = float(np.float32(r0) * np.float32(D))
-            y1 = float(np.float32(r1) * np.float32(D)) if r1 < gy else H
-            loc[:, 1] = (np.float32(y0) + np.float32(y1 - y0) * (loc[:, 1] / np.float32(H))).astype(np.float32)
-            row = fdist.column_of(loc[:, 1], D)
-            off = (row < r0) | (row >= r1)
-            loc[off, 1] = np.float32(0.5 * (y0 + y1))
-        id_base = rank * n_local
-    # pinned host buffers: the host-side copy of the agents (what krABMaga's Schedule holds)
-    h_id = torch.arange(id_base, id_base + n_local, dtype=torch.int64).to(torch.uint32).pin_memory() \
-        if hasattr(torch, "uint32") else None
-    h_loc = torch.from_numpy(loc).pin_memory()
-    h_ld = torch.zeros((n_local, 2), dtype=torch.float32).pin_memory()
-    if h_id is None:
+            f = Field2D(W, H, D, True, capacity=cap, device=local_rank)
+            loc = make_birds(n_local, W, H, clustered)
+            id_base = 0
+        else:
+            f = fdist.DistField2D(W, H, D, capacity=cap, device=local_rank, rank=rank, world=world, tile_rows=args.tile_rows)
+            c0, c1, r0, r1 = f.tile()
+            x0 = float(np.float32(c0) * np.float32(D))
+            x1 = float(np.float32(c1) * np.float32(D)) if c1 < gx else W
+            loc = make_birds(n_local, W, H, clustered, x0, x1, seed=INIT_SEED + rank)
+            # f32 rounding at the strip edges: keep every generated bird inside the columns this rank owns
+            col = fdist.column_of(loc[:, 0], D)
+            off = (col < c0) | (col >= c1)
+            loc[off, 0] = np.float32(0.5 * (x0 + x1))
+            if args.tile_rows > 1:   # tiles: squeeze the y coordinates into the rows this rank owns
+                y0 = float(np.float32(r0) * np.float32(D))
+                y1 = float(np.float32(r1) * np.float32(D)) if r1 < gy else H
+                loc[:, 1] = (np.float32(y0) + np.float32(y1 - y0) * (loc[:, 1] / np.float32(H))).astype(np.float32)
+                row = fdist.column_of(loc[:, 1], D)
+                off = (row < r0) | (row >= r1)
+                loc[off, 1] = np.float32(0.5 * (y0 + y1))
+            id_base = rank * n_local
+        # pinned host buffers: the host-side copy of the agents (what krABMaga's Schedule holds)
         h_id = torch.from_numpy(np.arange(id_base, id_base + n_local, dtype=np.uint32).view(np.int32)).pin_memory()
-    f.set_objects_raw(n_local, h_id.data_ptr(), h_loc.data_ptr(), h_ld.data_ptr())
-    f.set_math_mode(args.math)
-    f.commit()  # lazy_update (+ first halo exchange on >1 GPU)
-    f.synchronize()
-    assert f.num_owned() == n_local, (f.num_owned(), n_local)
+        h_loc = torch.from_numpy(loc).pin_memory()
+        h_ld = torch.zeros((n_local, 2), dtype=torch.float32).pin_memory()
+        f.set_objects_raw(n_local, h_id.data_ptr(), h_loc.data_ptr(), h_ld.data_ptr())
+        f.set_math_mode(args.math)
+        f.commit()  # lazy_update (+ first halo exchange on >1 GPU)
+        f.synchronize()   # also the end of the pinned buffers' lifetime rule (include/flk.h)
+        assert f.num_owned() == n_local, (f.num_owned(), n_local)
+        return dict(f=f, W=W, H=H, gx=gx, gy=gy, n_total=n_total, n_local=n_local, cap=cap, loc=loc, id_base=id_base,
+                    label=label, clustered=clustered)
 
-    # ---- warm-up ----
-    f.run(0, args.warmup, STEP_SEED)
-    f.synchronize()
+    def timed_run(f, n_total, first, warmup, steps, sampler=None):
+        """W warm-up ticks, then K ticks timed on the device (CUDA events on the handle's stream, max over ranks)"""
+        f.run(first, warmup, STEP_SEED)
+        f.synchronize()
+        launches0 = f.launch_count()
+        f.profile_enable(1)   # CUDA events around every k_step launch of the timed region
+        if sampler is not None:
+            sampler.start()
+        barrier()
+        f.run(first + warmup, steps, STEP_SEED)
+        f.synchronize()
+        barrier()
+        ms = max_over_ranks(f.elapsed_ms())
+        clocks = sampler.stop() if sampler is not None else None
+        k_ms, k_n = f.profile_step_kernel()
+        f.profile_enable(False)
+        return dict(ms=ms, value=n_total * steps / (ms * 1e-3), k_ms=k_ms, k_n=k_n, clocks=clocks,
+                    launches=f.launch_count() - launches0)
 
-    # ---- timed region: K ticks, device-timed on the handle's stream, step kernel bracketed by events ----
-    launches0 = f.launch_count()
-    f.profile_enable(1)   # CUDA events around every k_step launch of the timed region
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    f.run(args.warmup, args.steps, STEP_SEED)
-    f.synchronize()
-    barrier()
-    ms = max_over_ranks(f.elapsed_ms())
-    clocks = sampler.stop() if rank == 0 else None
-    k_ms, k_n = f.profile_step_kernel()
-    f.profile_enable(False)
-    launches = f.launch_count() - launches0
-    # the other kernels of a tick (scan, scatter, rank), timed over a few more ticks outside the timed region
+    # ---- the benchmarked workload ----
+    wl = build_field(args.workload, args.birds_per_gpu)
+    f, W, H, n_total, n_local, cap, loc, id_base = (wl[k] for k in ("f", "W", "H", "n_total", "n_local", "cap", "loc", "id_base"))
+    clustered = wl["clustered"]
+    main = timed_run(f, n_total, 0, args.warmup, args.steps, ClockSampler(local_rank) if rank == 0 else None)
+    ms, value, clocks, launches = main["ms"], main["value"], main["clocks"], main["launches"]
+    # the other kernels of a tick, timed over a few more ticks outside the timed region
     f.profile_enable(2)
     f.run(args.warmup + args.steps, min(args.steps, 20), STEP_SEED)
     f.synchronize()
     rebin_ms = f.profile_rebin()
     f.profile_enable(False)
     n_now = sum_over_ranks(float(f.num_owned()))
-    value = n_total * args.steps / (ms * 1e-3)
 
     # roofline of the dominant kernel (k_step): algorithmic bytes per launch / average launch duration
-    k_avg_ms = max_over_ranks(k_ms / max(k_n, 1))
+    k_avg_ms = max_over_ranks(main["k_ms"] / max(main["k_n"], 1))
     peak, peak_src = measured_peak_gbs()
     achieved = ALGO_BYTES_PER_UPDATE * n_local / (k_avg_ms * 1e-3) / 1e9
     traffic = ncu_traffic_per_launch(n_total // world)
@@ -330,14 +415,15 @@ def run_ours(args, world: int, rank: int, local_rank: int):
 
     # ---- e2e: per step, host -> device copy of every agent, one tick, device -> host read of the new state ----
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
-    e2e_extra = {}
+    reps = max(1, args.e2e_reps)
     if world == 1:
         # The host keeps the agents as a list indexed by id (flockers/src/model/state.rs:40-51), so the dense C-ABI
-        # calls move Bird minus its id: 16 B per bird each way.  Every step of every repetition uploads all agents
-        # from pinned host memory, publishes them (lazy_update), runs Bird::step + lazy_update and downloads all
-        # agents; the download is the next step's upload (a dependent chain per repetition).  `reps` independent
-        # repetitions (simulate!'s third argument, flockers/src/main.rs:47) are pipelined over one handle each, so
-        # one repetition's download overlaps the next one's upload on the two PCIe directions.
+        # calls move Bird minus its id: 16 B per bird each way.  Every step uploads all agents from pinned host memory,
+        # publishes them (lazy_update), runs Bird::step + lazy_update and downloads all agents; the download is the next
+        # step's upload (a dependent chain).  The headline is ONE repetition, what the reference ships
+        # (simulate_old!(state, step, 1), flockers/src/main.rs:47); `pipelined_value` runs `reps` independent
+        # repetitions (simulate!'s third argument) over one handle each, so that one repetition's download overlaps the
+        # next one's upload on the two PCIe directions.
         rec0 = np.concatenate([loc, np.zeros_like(loc)], axis=1)
 
         def e2e_run(fields, steps):
@@ -367,25 +453,21 @@ def run_ours(args, world: int, rank: int, local_rank: int):
                 assert not bool(torch.isnan(h_in[r][:: max(n_local // 4096, 1)]).any())
             return R * n_local * steps / dt
 
-        serial_value = e2e_run([f], e2e_steps)
-        reps = max(1, args.e2e_reps)
+        e2e_value = e2e_run([f], e2e_steps)
         extra = [Field2D(W, H, D, True, capacity=cap, device=local_rank) for _ in range(reps - 1)]
         for fx in extra:
             fx.set_math_mode(args.math)
-        e2e_value = e2e_run([f] + extra, e2e_steps)
+        pipelined = e2e_run([f] + extra, e2e_steps) if reps > 1 else e2e_value
         for fx in extra:
             fx.close()
         e2e_bytes = 16 * n_local
-        e2e_extra = {"reps": reps, "serial_value": serial_value,
-                     "what": f"{reps} independent repetitions pipelined over {reps} handles; per step and repetition: "
-                             "flk_set_objects_dense(pinned host, 16 B/bird) + lazy_update + Bird::step + lazy_update + "
-                             "flk_snapshot_dense_async(pinned host, 16 B/bird); output feeds the next step's input; "
-                             "serial_value = one repetition alone (no overlap)"}
+        e2e_what = ("ONE repetition (flockers/src/main.rs:47): per step flk_set_objects_dense(pinned host, 16 B/bird) + "
+                    "lazy_update + Bird::step + lazy_update + flk_snapshot_dense_async(pinned host, 16 B/bird); the output "
+                    f"feeds the next step's input; pipelined_value = {reps} independent repetitions over {reps} handles")
     else:
         # One strip per rank: the birds a rank owns change with migration, so ids travel with the records (20 B per
-        # bird each way).  `reps` independent repetitions, each its own group of strip handles (own NCCL communicator),
-        # are pipelined like the single-GPU case; every rank walks the repetitions in the same order (collectives).
-        reps = max(1, args.e2e_reps)
+        # bird each way).  Headline: one repetition; pipelined_value: `reps` independent repetitions, each its own group
+        # of strip handles (own NCCL communicator); every rank walks the repetitions in the same order (collectives).
         cap_h = n_local + n_local // 8 + 65536
 
         def e2e_run_dist(fields, steps):
@@ -430,22 +512,42 @@ def run_ours(args, world: int, rank: int, local_rank: int):
                  for _ in range(reps - 1)]
         for fx in extra:
             fx.set_math_mode(args.math)
-        serial_value = e2e_run_dist([f], e2e_steps)
-        e2e_value = e2e_run_dist([f] + extra, e2e_steps)
+        e2e_value = e2e_run_dist([f], e2e_steps)
+        pipelined = e2e_run_dist([f] + extra, e2e_steps) if reps > 1 else e2e_value
         for fx in extra:
             fx.close()
         e2e_bytes = 20 * (n_total // world)
-        e2e_extra = {"reps": reps, "serial_value": serial_value,
-                     "what": f"{reps} independent repetitions pipelined over {reps} groups of strip handles; per rank, step and "
-                             "repetition: flk_set_objects(pinned host, 20 B/bird) + commit + Bird::step + exchange + "
-                             "lazy_update + flk_dist_snapshot_owned_async(pinned host, 20 B/bird); output feeds the next "
-                             "step's input; bytes are per rank; serial_value = one repetition alone"}
+        e2e_what = ("ONE repetition: per rank and step flk_set_objects(pinned host, 20 B/bird) + commit + Bird::step + "
+                    "exchange + lazy_update + flk_dist_snapshot_owned_async(pinned host, 20 B/bird); the output feeds the "
+                    f"next step's input; bytes are per rank; pipelined_value = {reps} independent repetitions over {reps} "
+                    "groups of strip handles")
+    f.close()
+
+    # ---- parity leg: every bench line carries a correctness check of the code that was just timed ----
+    parity = parity_check(args, world, rank, local_rank) if not args.no_verify else None
+
+    # ---- the other BASELINE configs, short legs (driver-visible numbers for configs 2, 3 and 5) ----
+    extras = {}
+    if not args.no_extras and args.workload == "weak16m" and args.birds_per_gpu is None:
+        legs = [("1m", 200), ("clustered", 10)] if world == 1 else [("strong16m", 100)]
+        for name, k in legs:
+            try:
+                w2 = build_field(name, None)
+                r2 = timed_run(w2["f"], w2["n_total"], 0, 10, k)
+                extras[name] = {"value": r2["value"], "unit": "bird-updates/s", "ms_per_step": r2["ms"] / k, "steps": k,
+                                "warmup": 10, "workload": w2["label"], "birds_after": int(sum_over_ranks(float(w2["f"].num_owned()))),
+                                "k_step_ms": max_over_ranks(r2["k_ms"] / max(r2["k_n"], 1))}
+                w2["f"].close()
+            except Exception as e:   # an extra leg never takes the headline down with it
+                extras[name] = {"error": repr(e)}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on the host cores, bounded sample ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, threads, sample = cpu_oracle_run(args.cpu_birds, args.cpu_ticks, 1, clustered)
-        cpu = {"value": v, "unit": "bird-updates/s", "cores": threads, "kind": "port", "sample": sample}
+        gx, gy, n, whole = cpu_sample_geometry(args.workload, 1, args.birds_per_gpu, args.cpu_birds)
+        v, dt, threads, sample = cpu_oracle_run(gx, gy, n, args.cpu_ticks, 1, clustered)
+        cpu = {"value": v, "unit": "bird-updates/s", "cores": threads, "kind": "port",
+               "sample": ("the whole workload: " if whole else "bounded sample of the workload: ") + sample}
 
     if rank == 0:
         line = {
@@ -453,14 +555,12 @@ def run_ours(args, world: int, rank: int, local_rank: int):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong" if args.workload == "strong16m" else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": label, "birds_total": n_total, "birds_per_gpu": n_total // world,
-                       "decomposition": "single GPU" if world == 1 else
-                                        (f"x-strips over {world} GPUs, NCCL halo+migration" if args.tile_rows == 1 else
-                                         f"{world // args.tile_rows} x {args.tile_rows} tiles over {world} GPUs, NCCL halo+migration in two hops"),
-                       "math": "exact (IEEE f32, bit-identical to the oracle)" if args.math == 0 else "fast",
-                       "l2": "inputs larger than L2 (>=20 B/bird x birds per GPU vs 126 MB)" if n_total // world >= 8_000_000
-                             else "working set fits L2 (reference config size)",
-                       "birds_after": int(n_now)},
+            "config": common_config(args, world),
+            "details": {"decomposition": "single GPU" if world == 1 else
+                                         (f"x-strips over {world} GPUs, NCCL halo+migration" if args.tile_rows == 1 else
+                                          f"{world // args.tile_rows} x {args.tile_rows} tiles over {world} GPUs, NCCL halo+migration in two hops"),
+                        "math": "exact (IEEE f32, bit-identical to the oracle)" if args.math == 0 else "fast",
+                        "birds_after": int(n_now)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_step", "kernel_ms": k_avg_ms,
                          "kernel_share_of_step": k_avg_ms / (ms / args.steps), "peak_source": peak_src,
@@ -470,14 +570,103 @@ def run_ours(args, world: int, rank: int, local_rank: int):
                          "note": "path is FP32-issue bound, not HBM bound (DESIGN.md roofline): see issue_slots"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "bird-updates/s", "h2d_bytes_per_step": e2e_bytes,
-                    "d2h_bytes_per_step": e2e_bytes, "steps": e2e_steps, **e2e_extra},
+                    "d2h_bytes_per_step": e2e_bytes, "steps": e2e_steps, "reps": 1, "pipelined_value": pipelined,
+                    "pipelined_reps": reps, "what": e2e_what},
+            "parity_check": parity,
+            "extra_configs": extras,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    f.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_check(args, world: int, rank: int, local_rank: int):
+    """Correctness of the code that was just timed, inside the bench line.
+    N = 1: the CUDA path against the CPU oracle, 200 000 birds, 3 ticks, whole population bit for bit.
+    N > 1: 1 M birds (BASELINE config 2 geometry) as `world` strips over NCCL against the single field on rank 0's GPU
+           AND against the oracle, 4 ticks, bit for bit; the digest is the sha256 of the id-sorted final state."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from examples_b200 import Field2D
+    try:
+        if world == 1:
+            cells, n, ticks = 212, 200_000, 3
+        else:
+            cells, n, ticks = 480, 1_000_000, 4
+        Wp = field_size(cells)
+        loc = make_birds(n, Wp, Wp, False, seed=INIT_SEED + 77)
+        ids = np.arange(n, dtype=np.uint32)
+        ld = np.zeros_like(loc)
+        got = None
+        if world > 1:
+            from examples_b200 import distributed as fdist
+            fd = fdist.DistField2D(Wp, Wp, D, capacity=n // world * 2 + 65536, device=local_rank, rank=rank, world=world,
+                                   tile_rows=args.tile_rows)
+            c0, c1, r0, r1 = fd.tile()
+            col, row = fdist.column_of(loc[:, 0], D), fdist.column_of(loc[:, 1], D)
+            mine = (col >= c0) & (col < c1) & (row >= r0) & (row < r1)
+            fd.set_objects(ids[mine], loc[mine], ld[mine])
+            fd.set_math_mode(args.math)
+            fd.commit()
+            fd.run(0, ticks, STEP_SEED)
+            o_id, o_loc, o_ld = fd.snapshot_owned()
+            fd.close()
+            k = torch.tensor([len(o_id)], dtype=torch.int64, device="cuda")
+            ks = [torch.zeros_like(k) for _ in range(world)]
+            dist.all_gather(ks, k)
+            kmax = int(max(int(t.item()) for t in ks))
+            pack = np.zeros((kmax, 5), dtype=np.float32)
+            pack[: len(o_id), 0] = o_id.view(np.float32)
+            pack[: len(o_id), 1:3] = o_loc
+            pack[: len(o_id), 3:5] = o_ld
+            mine_t = torch.from_numpy(pack).cuda()
+            parts = [torch.zeros_like(mine_t) for _ in range(world)]
+            dist.all_gather(parts, mine_t)
+            if rank == 0:
+                rows = np.concatenate([p.cpu().numpy()[: int(kk.item())] for p, kk in zip(parts, ks)])
+                o = np.argsort(rows[:, 0].view(np.uint32), kind="stable")
+                got = np.ascontiguousarray(rows[o])
+        if rank != 0:
+            return None
+        f1 = Field2D(Wp, Wp, D, True, capacity=n, device=local_rank)
+        f1.set_objects(ids, loc, ld)
+        f1.set_math_mode(args.math)
+        f1.lazy_update()
+        f1.run(0, ticks, STEP_SEED)
+        s_id, s_loc, s_ld = f1.snapshot_by_id()
+        f1.close()
+        single = np.zeros((n, 5), dtype=np.float32)
+        single[:, 0] = s_id.view(np.float32)
+        single[:, 1:3], single[:, 3:5] = s_loc, s_ld
+        from oracle import oracle as O
+        b = np.zeros(n, dtype=O.BIRD)
+        b["id"], b["x"], b["y"] = ids, loc[:, 0], loc[:, 1]
+        sim = O.Sim(Wp, Wp)
+        sim.init(b)
+        for _ in range(ticks):
+            sim.step(seed=STEP_SEED, threads=os.cpu_count() or 1)
+        a = sim.agents()
+        orc = np.zeros((n, 5), dtype=np.float32)
+        orc[:, 0] = a["id"].view(np.float32)
+        orc[:, 1], orc[:, 2], orc[:, 3], orc[:, 4] = a["x"], a["y"], a["ldx"], a["ldy"]
+        same = lambda u, v: u.shape == v.shape and np.array_equal(u.view(np.uint32), v.view(np.uint32))
+        res = {"birds": n, "ticks": ticks, "cells": f"{cells}x{cells}",
+               "digest": hashlib.sha256(single.view(np.uint8).tobytes()).hexdigest()[:16],
+               "single_gpu_vs_oracle": "bit-exact" if (args.math == 0 and same(single, orc)) else
+                                       ("fast math: max abs err %.3g" % float(np.abs(single[:, 1:] - orc[:, 1:]).max())
+                                        if args.math else "MISMATCH")}
+        ok = res["single_gpu_vs_oracle"] != "MISMATCH"
+        if world > 1:
+            res["strips_over_nccl_vs_single_gpu"] = "bit-exact" if same(got, single) else "MISMATCH"
+            res["ranks"] = world
+            ok = ok and res["strips_over_nccl_vs_single_gpu"] == "bit-exact"
+        res["status"] = "ok" if ok else "FAILED"
+        return res
+    except Exception as e:
+        return {"status": "FAILED", "error": repr(e)}
 
 
 def main():
@@ -492,9 +681,11 @@ def main():
     ap.add_argument("--tile-rows", type=int, default=1)   # > 1: split the rows too (tiles); default = x-strips
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-reps", type=int, default=3)           # independent repetitions pipelined in the e2e leg
-    ap.add_argument("--cpu-birds", type=int, default=1_000_000)   # birds of the CPU sample (per tick)
-    ap.add_argument("--cpu-ticks", type=int, default=200)        # ~10 s of CPU work on 16 cores
+    ap.add_argument("--cpu-birds", type=int, default=CPU_BIRDS_CAP)   # largest population the CPU arm steps per tick
+    ap.add_argument("--cpu-ticks", type=int, default=12)         # cpu_baseline leg of our arm: ~10 s on 16 cores at 16 M birds
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")          # skip the parity leg
+    ap.add_argument("--no-extras", action="store_true")          # skip the short legs on the other BASELINE configs
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -52,6 +52,8 @@ int field_alloc(flk_field *f) {
     CUDA_TRY(cudaMalloc(&s.n_read_dev, 4));
     CUDA_TRY(cudaMalloc(&s.err_flag, 4));
     CUDA_TRY(cudaMemsetAsync(s.err_flag, 0, 4, f->stream));
+    CUDA_TRY(cudaHostAlloc(&f->h_err, 4, cudaHostAllocDefault));
+    *f->h_err = 0;
     if (s.pw) {
         CUDA_TRY(cudaMalloc(&s.pay, cap * s.pw * 4));
         CUDA_TRY(cudaMalloc(&s.tpay, capw * s.pw * 4));
@@ -73,6 +75,7 @@ void field_free(flk_field *f) {
     if (f->d_paystage) cudaFree(f->d_paystage);
     if (f->d_injected) cudaFree(f->d_injected);
     if (f->h_dense) cudaFreeHost(f->h_dense);
+    if (f->h_err) cudaFreeHost(f->h_err);
     if (f->frame_rec) cudaFree(f->frame_rec);
     if (f->frame_ids) cudaFree(f->frame_ids);
     if (f->ev_frame_ready) cudaEventDestroy(f->ev_frame_ready);
@@ -270,9 +273,11 @@ int flk_field_clear(flk_field *f) {
     CUDA_TRY(cudaMemsetAsync(f->s.cell_start, 0, m * 4, f->stream));
     CUDA_TRY(cudaMemsetAsync(f->s.cnt, 0, m * 4, f->stream));
     CUDA_TRY(cudaMemsetAsync(f->s.n_read_dev, 0, 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(f->s.err_flag, 0, 4, f->stream));
     f->n_read = 0; f->w_count = 0;
     f->pend_id.clear(); f->pend_loc.clear(); f->pend_ld.clear();
     f->graph_valid = false;
+    if (f->dist) dist_reset_counts(f);
     return FLK_OK;
 }
 
@@ -653,7 +658,11 @@ int flk_get_neighbors_within_distance(flk_field *f, float x, float y, float dist
 
 int flk_synchronize(flk_field *f) {
     CHECK_HANDLE(f);
+    // device-side error bits (a message or a rank over its capacity, a launch that did not cover its range) are
+    // reported here, whatever call enqueued the work that raised them
+    CUDA_TRY(cudaMemcpyAsync(f->h_err, f->s.err_flag, 4, cudaMemcpyDeviceToHost, f->stream));
     CUDA_TRY(cudaStreamSynchronize(f->stream));
+    if (*f->h_err) return report_device_errors(f, *f->h_err);
     if (f->dense_pending) {   // outcome of the last (possibly asynchronous) dense snapshot
         f->dense_pending = false;
         if (*f->h_dense)
@@ -759,6 +768,16 @@ int flk_host_free(void *p) {
 }  // extern "C"
 
 namespace flk {
+
+int report_device_errors(flk_field *f, uint32_t flag) {
+    if (flag & ERR_CAPACITY)
+        return fail(FLK_E_CAPACITY, "the field holds more objects than its capacity %llu (objects were dropped; the state is invalid)",
+                    (unsigned long long)f->cap);
+    if (flag & ERR_EXCHANGE)
+        return fail(FLK_E_CAPACITY, "a halo/migration message exceeded %u birds or a launch did not cover its range "
+                                    "(birds were dropped or not stepped; the state is invalid)", f->s.capx);
+    return fail(FLK_E_STATE, "device error bits 0x%x", flag);
+}
 
 int upload_injected(flk_field *f, const float *r, uint64_t n) {
     if (n == 0) return FLK_OK;

@@ -458,16 +458,25 @@ static int dist_publish_uploads(flk_field *f) {
     return FLK_OK;
 }
 
+// the population changes outside the tick loop (upload, clear): forget what the host knew about it.  A count copy
+// enqueued before the change may still land later; it must not become `known` (it would under-size the interior grid)
+void dist_reset_counts(flk_field *f) {
+    flk_dist_state *d = f->dist;
+    d->committed = false;
+    d->have_known = false;
+    d->count_pending = false;
+    d->known = 0; d->known_tick = 0; d->copy_tick = 0; d->tick_no = 0;
+}
+
 int dist_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld) {
-    f->dist->committed = false;
-    f->dist->have_known = false;   // the population is about to change outside the tick loop
+    dist_reset_counts(f);
     return write_append(f, n, id, loc, ld);
 }
 
 static int dist_check_errors(flk_field *f) {
-    uint32_t flag = 0;
-    CUDA_TRY(cudaMemcpyAsync(&flag, f->s.err_flag, 4, cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(cudaMemcpyAsync(f->h_err, f->s.err_flag, 4, cudaMemcpyDeviceToHost, f->stream));
     CUDA_TRY(cudaStreamSynchronize(f->stream));
+    const uint32_t flag = *f->h_err;
     if (flag & ERR_CAPACITY) return fail(FLK_E_CAPACITY, "rank %d holds more birds than its capacity %llu", f->dist->rank, (unsigned long long)f->cap);
     if (flag & ERR_EXCHANGE) return fail(FLK_E_CAPACITY, "rank %d: halo/migration message exceeded %u birds", f->dist->rank, f->s.capx);
     return FLK_OK;

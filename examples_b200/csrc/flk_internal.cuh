@@ -31,6 +31,7 @@ struct flk_field {
     cudaStream_t frame_stream = nullptr;
     cudaEvent_t ev_frame_ready = nullptr, ev_frame_done = nullptr;
     bool frame_pending = false;
+    uint32_t *h_err = nullptr;        // pinned word: device error bits (ERR_*) as of the last flk_synchronize
     uint32_t *h_dense = nullptr;      // pinned word: ids outside the range of the last dense snapshot
     bool dense_pending = false;
     uint64_t injected_cap = 0;
@@ -80,5 +81,7 @@ void dist_free(flk_field *f);
 int dist_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld);
 int dist_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed);
 int dist_refresh_counts(flk_field *f);
+void dist_reset_counts(flk_field *f);
+int report_device_errors(flk_field *f, uint32_t flag);
 
 }  // namespace flk

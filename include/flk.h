@@ -18,6 +18,12 @@
  *   - the library owns all device memory; host arrays passed in stay owned by the caller.
  *   - there is NO CPU fallback: without a CUDA device every compute call fails with FLK_E_CUDA.
  *   - `float2`-shaped arguments are plain `const float*` with x,y interleaved (Real2D{x,y}).
+ *   - host buffer lifetime: calls that take HOST arrays (flk_set_objects*, flk_step's injected_r, flk_query_batch)
+ *     enqueue their copies on the handle's stream.  From pageable memory the copy is staged before the call returns;
+ *     from PINNED memory (flk_host_alloc, cudaHostAlloc, torch pin_memory) it runs asynchronously, so such a buffer
+ *     must stay untouched until the next flk_synchronize on that handle returns.
+ *   - device-side failures (a rank or a message over its capacity) are reported by the next flk_synchronize,
+ *     flk_dist_num_owned or snapshot call as FLK_E_CAPACITY; the field contents are undefined afterwards.
  */
 #ifndef FLK_H
 #define FLK_H
@@ -63,7 +69,12 @@ int flk_field_clear(flk_field *f);
 int flk_set_params(flk_field *f, float cohesion, float avoidance, float randomness, float consistency,
                    float momentum, float jump, float radius, int relax);
 
-/* 0 = exact (default): IEEE f32, no FMA contraction — bit-identical to the reference arithmetic.
+/* 0 = exact (default): every f32 operation of Bird::step is one IEEE-754 round-to-nearest operation, no FMA
+ *     contraction, evaluated in the reference's order with the neighbours of a cell visited in ascending id (the
+ *     canonical bag order).  Results are bit-identical to the repository's CPU oracle (oracle/), which
+ *     restates bird.rs line by line; they equal a krABMaga run bit for bit only when its bags are in that order too
+ *     (the engine's bag order is the schedule's execution order, which it leaves unspecified) — otherwise the f32
+ *     sums differ in their last bits (quantified by tests/test_oracle.py::test_bag_order_sensitivity_is_within_tolerance).
  * 1 = fast: reciprocal-based division in the neighbour loop (<= 2 ulp per term, same order). */
 int flk_set_math_mode(flk_field *f, int mode);
 
@@ -95,7 +106,7 @@ int flk_lazy_update(flk_field *f);
  * Randomness (bird.rs:103-107): if injected_r != NULL it is a HOST array of n_injected (r1,r2) pairs,
  * the pair of bird `id` at [2*id],[2*id+1] (ids >= n_injected fall back to Philox);
  * else Philox4x32-10 with key=seed, counter=(id,step,0), r = (out >> 8) * 2^-24.
- * Asynchronous on the handle's stream (injected_r is copied before returning). */
+ * Asynchronous on the handle's stream (injected_r: see "host buffer lifetime" above). */
 int flk_step(flk_field *f, uint64_t step, uint64_t seed, const float *injected_r, uint64_t n_injected);
 
 /* `simulate!(state, n_steps, 1)` inner loop (flockers/src/main.rs:47): n_steps x { step ; lazy_update },
