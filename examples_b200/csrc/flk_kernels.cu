@@ -478,7 +478,7 @@ __device__ __noinline__ void step_bird_general(const Geom &g, const Params &p, c
     // cells are < 2d apart and dim >= 6d, so the plain difference is the toroidal one (exactly).
     const bool interior = g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && gcx >= 1 && gcx <= g.mx - 2 &&
                           cy >= 1 && cy <= g.my - 2 && d_ok;
-    // both queries return nothing for dist <= 0 (`if dist <= 0 -> []`; k_query and the oracle agree):
+    // both queries return nothing for dist <= 0 (`if dist <= 0 -> []`; k_query does the same):
     // the bird then sees no neighbour, draws nothing and keeps only its momentum (bird.rs:42)
     if (p.radius <= 0.0f) { /* acc stays empty */ }
     else if (interior && RELAX) accumulate_interior<MATH>(g, s, me, i, lc, lr, acc);
