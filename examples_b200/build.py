@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libflk.so")
-SOURCES = ["flk_kernels.cu", "flk_api.cu", "flk_dist.cu"]
-HEADERS = ["flk_device.cuh", "flk_kernels.cuh", "flk_internal.cuh", os.path.join("..", "..", "include", "flk.h")]
+SOURCES = ["flk_kernels.cu", "flk_slots.cu", "flk_api.cu", "flk_dist.cu"]
+HEADERS = ["flk_device.cuh", "flk_kernels.cuh", "flk_step.cuh", "flk_slots.cuh", "flk_internal.cuh", os.path.join("..", "..", "include", "flk.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

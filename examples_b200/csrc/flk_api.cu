@@ -62,6 +62,151 @@ int field_alloc(flk_field *f) {
     CUDA_TRY(cudaMemsetAsync(s.cnt, 0, mp * 4, f->stream));
     CUDA_TRY(cudaMemsetAsync(s.step_dev, 0, 8, f->stream));
     CUDA_TRY(cudaMemsetAsync(s.n_read_dev, 0, 4, f->stream));
+    return slots_alloc(f);
+}
+
+// ---- the fixed-capacity-cell layout (flk_slots.cuh): allocation and the switches between the two layouts -----------
+static int slot_env_C() {
+    const char *e = getenv("FLK_SLOT_C");
+    const int c = e ? atoi(e) : 16;
+    return (c == 4 || c == 8 || c == 12 || c == 16) ? c : 16;
+}
+
+int slots_alloc(flk_field *f) {
+    Geom &g = f->g;
+    f->slot_capable = false;
+    f->layout = 0;
+    if (const char *e = getenv("FLK_LAYOUT")) {
+        if (!strcmp(e, "runs")) f->layout_pref = 0;
+        else if (!strcmp(e, "slots")) f->layout_pref = 1;
+    }
+    // what never changes for a handle: rows not split (tiles keep the sorted runs), toroidal field, Bird-sized objects,
+    // and a capacity that does not exceed half the slots of the owned cells even when spread evenly
+    if (g.mode != 0 || !g.toroidal || f->s.pw != 0 || f->layout_pref == 0) return FLK_OK;
+    const int C = slot_env_C();
+    const double owned_cells = (double)(g.mode == 0 ? g.mx : g.nown) * (double)g.my;
+    if (f->layout_pref != 1 && (double)f->cap > owned_cells * (C / 2)) return FLK_OK;
+    SlotStore &S = f->S;
+    const uint64_t ncell = f->ncell, ncols = (uint64_t)g.ncols;
+    const uint64_t per_col = (f->cap + (uint64_t)(g.mode == 0 ? g.mx : g.nown) - 1) / (uint64_t)(g.mode == 0 ? g.mx : g.nown);
+    uint64_t stride = 8 * ((per_col + SLOT_CHUNK - 1) / SLOT_CHUNK) + 8;
+    if (stride < 16) stride = 16;
+    if (stride > 65536) stride = 65536;
+    S.C = C; S.rd = 0; S.stride = (uint32_t)stride; S.spill_cap = (uint32_t)f->cap;
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(cudaMalloc(&S.rec[b], ncell * C * sizeof(float4)));
+        CUDA_TRY(cudaMalloc(&S.id[b], ncell * C * 4));
+        CUDA_TRY(cudaMalloc(&S.cnt[b], (ncell + 1) * 4));
+        CUDA_TRY(cudaMalloc(&S.spill[b], (uint64_t)S.spill_cap * sizeof(SpillEntry)));
+        CUDA_TRY(cudaMemsetAsync(S.cnt[b], 0, (ncell + 1) * 4, f->stream));
+    }
+    CUDA_TRY(cudaMalloc(&S.spill_cnt, 8));
+    CUDA_TRY(cudaMalloc(&S.perm, ncell * 8));
+    CUDA_TRY(cudaMalloc(&S.colcount, ncols * 4));
+    CUDA_TRY(cudaMalloc(&S.colmax, ncols * 4));
+    CUDA_TRY(cudaMalloc(&S.colchunk, (ncols + 1) * 4));
+    CUDA_TRY(cudaMalloc(&S.coltab, ncols * stride * 4));
+    CUDA_TRY(cudaMalloc(&S.totals, 16));
+    CUDA_TRY(cudaMalloc(&S.ticket, 4));
+    CUDA_TRY(cudaMalloc(&S.dbg, 64));
+    CUDA_TRY(cudaMemsetAsync(S.dbg, 0, 64, f->stream));
+    CUDA_TRY(cudaMalloc(&f->d_stats, 8));
+    CUDA_TRY(cudaHostAlloc(&f->h_totals, 16, cudaHostAllocDefault));
+    memset(f->h_totals, 0, 16);
+    CUDA_TRY(cudaMemsetAsync(S.spill_cnt, 0, 8, f->stream));
+    CUDA_TRY(cudaMemsetAsync(S.colcount, 0, ncols * 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(S.colmax, 0, ncols * 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(S.colchunk, 0, (ncols + 1) * 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(S.totals, 0, 16, f->stream));
+    CUDA_TRY(cudaMemsetAsync(S.ticket, 0, 4, f->stream));
+    f->slot_capable = true;
+    return FLK_OK;
+}
+
+static void slots_free(flk_field *f) {
+    SlotStore &S = f->S;
+    for (int b = 0; b < 2; ++b) { cudaFree(S.rec[b]); cudaFree(S.id[b]); cudaFree(S.cnt[b]); cudaFree(S.spill[b]); }
+    cudaFree(S.spill_cnt); cudaFree(S.perm); cudaFree(S.colcount); cudaFree(S.colmax); cudaFree(S.colchunk);
+    cudaFree(S.coltab); cudaFree(S.totals); cudaFree(S.ticket); cudaFree(S.dbg);
+    if (f->d_stats) cudaFree(f->d_stats);
+    if (f->h_totals) cudaFreeHost(f->h_totals);
+    for (int b = 0; b < 2; ++b) if (f->sgraph[b]) cudaGraphExecDestroy(f->sgraph[b]);
+}
+
+// the parameters the slotted step kernel's tile path is written for (anything else runs on the sorted-runs layout)
+bool slots_params_ok(const flk_field *f) {
+    const Geom &g = f->g;
+    const Params &p = f->p;
+    return p.relax && p.k == 1 && p.radius > 0.0f && g.toroidal && g.mx >= 6 && g.my >= 6 && g.d >= 0x1p-20f && g.d <= 4096.0f;
+}
+
+// loose bound of the largest column's population: the largest column of a recent READ buffer (copied back after every
+// lazy_update, possibly a few ticks old) or the mean, plus 3 %.  It only sizes the step kernel's grid.
+uint32_t slot_col_bound(const flk_field *f) {
+    const uint64_t cols = (uint64_t)(f->g.mode == 0 ? f->g.mx : f->g.nown);
+    uint64_t est = (f->n_read + cols - 1) / (cols ? cols : 1);
+    if (f->h_totals && f->h_totals[1] > est) est = f->h_totals[1];
+    return (uint32_t)(est + est / 32 + 128);
+}
+
+// Field2D::lazy_update on the slotted store: the WRITE buffer becomes READ
+int slots_publish(flk_field *f, int bump_step) {
+    launch_slot_colscan(f->g, f->S, f->s, (uint32_t)f->g.ncols, bump_step, f->stream);
+    f->S.rd ^= 1;
+    CUDA_TRY(cudaMemcpyAsync(f->h_totals, f->S.totals, 16, cudaMemcpyDeviceToHost, f->stream));
+    f->launches += 1;
+    f->view_valid = false;
+    CUDA_TRY(cudaGetLastError());
+    return FLK_OK;
+}
+
+// read-side calls work on the sorted runs: build them from the slotted READ buffer when they are stale
+int ensure_view(flk_field *f) {
+    if (f->layout != 1 || f->view_valid) return FLK_OK;
+    CUDA_TRY(cudaMemcpyAsync(f->s.cnt, f->S.cnt[f->S.rd], (uint64_t)f->ncell * 4, cudaMemcpyDeviceToDevice, f->stream));
+    launch_scan(f->s, f->ncell + 1, f->stream);            // -> cell_start; leaves s.cnt zeroed again
+    launch_slot_materialize(f->g, slot_args(f->S), f->s, f->ncell, f->stream);
+    f->launches += 4;
+    CUDA_TRY(cudaGetLastError());
+    f->view_valid = true;
+    return FLK_OK;
+}
+
+// leave the slotted layout (too many spilled birds, or parameters its step kernel is not written for).  Only between a
+// lazy_update and the next write: the slotted WRITE buffer must be empty.
+int demote_to_runs(flk_field *f) {
+    if (f->layout != 1) return FLK_OK;
+    if (f->w_count != 0) return fail(FLK_E_STATE, "layout change with a non-empty WRITE buffer (call flk_lazy_update first)");
+    int rc = ensure_view(f);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(f->S.cnt[f->S.rd], 0, ((uint64_t)f->ncell + 1) * 4, f->stream));
+    CUDA_TRY(cudaMemsetAsync(f->S.spill_cnt, 0, 8, f->stream));
+    f->layout = 0;
+    f->view_valid = false;
+    f->graph_valid = false;
+    return FLK_OK;
+}
+
+// enter the slotted layout when the freshly published sorted-runs READ buffer fits it (single GPU: decided with one small
+// synchronising read right after an upload was published)
+int maybe_promote_to_slots(flk_field *f) {
+    if (!f->slot_capable || f->layout != 0 || f->w_count != 0 || f->layout_pref == 0 || !slots_params_ok(f)) return FLK_OK;
+    if (f->n_read == 0) return FLK_OK;
+    uint32_t st[2] = {0, 0};
+    CUDA_TRY(cudaMemsetAsync(f->d_stats, 0, 8, f->stream));
+    launch_cell_stats(f->s, f->ncell, f->S.C, f->d_stats, f->stream);
+    CUDA_TRY(cudaMemcpyAsync(st, f->d_stats, 8, cudaMemcpyDeviceToHost, f->stream));
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    const uint64_t limit = f->n_read / 4096 > 64 ? f->n_read / 4096 : 64;
+    if (f->layout_pref != 1 && st[1] > limit) return FLK_OK;   // clustered: the sorted runs handle any density
+    launch_slot_ingest_dense(f->g, slot_args(f->S), f->s, (uint32_t)f->n_read, 0, reinterpret_cast<const float4 *>(f->s.rec),
+                             f->s.ids, f->stream);
+    f->launches += 2;
+    int rc = slots_publish(f, 0);
+    if (rc) return rc;
+    f->layout = 1;
+    f->view_valid = true;      // rec / ids / cell_start still describe this very READ buffer
+    f->graph_valid = false;
     return FLK_OK;
 }
 
@@ -76,6 +221,7 @@ void field_free(flk_field *f) {
     if (f->d_injected) cudaFree(f->d_injected);
     if (f->h_dense) cudaFreeHost(f->h_dense);
     if (f->h_err) cudaFreeHost(f->h_err);
+    slots_free(f);
     if (f->frame_rec) cudaFree(f->frame_rec);
     if (f->frame_ids) cudaFree(f->frame_ids);
     if (f->ev_frame_ready) cudaEventDestroy(f->ev_frame_ready);
@@ -151,10 +297,12 @@ int write_append(flk_field *f, uint64_t n, const uint32_t *id, const float *loc,
     CUDA_TRY(cudaMemcpyAsync(d_id, id, n * 4, cudaMemcpyHostToDevice, f->stream));
     CUDA_TRY(cudaMemcpyAsync(d_loc, loc, n * 8, cudaMemcpyHostToDevice, f->stream));
     CUDA_TRY(cudaMemcpyAsync(d_ld, ld, n * 8, cudaMemcpyHostToDevice, f->stream));
-    launch_ingest(f->g, f->s, (uint32_t)n, d_id, d_loc, d_ld, d_pay, (uint32_t)f->w_count, 1, f->stream);
+    if (f->layout == 1) launch_slot_ingest(f->g, slot_args(f->S), f->s, (uint32_t)n, d_id, d_loc, d_ld, 1, f->stream);
+    else launch_ingest(f->g, f->s, (uint32_t)n, d_id, d_loc, d_ld, d_pay, (uint32_t)f->w_count, 1, f->stream);
     f->launches += 1;
     CUDA_TRY(cudaGetLastError());
     f->w_count += n;
+    f->uploaded = true;
     return FLK_OK;
 }
 
@@ -169,6 +317,21 @@ int enqueue_lazy_update(flk_field *f, int bump_step) {
         CUDA_TRY(cudaEventRecord(e, f->stream));
         return FLK_OK;
     };
+    if (f->layout == 1) {   // slotted: one pass over the cell counters (profile: all of it counted as "scan")
+        if (int rc = mark()) return rc;
+        if (int rc = slots_publish(f, bump_step)) return rc;
+        for (int k = 0; k < 3; ++k) if (int rc = mark()) return rc;
+        f->n_read = f->w_count;
+        f->w_count = 0;
+        if (f->uploaded && !f->capturing && f->g.mode == 0) {
+            // an upload was published: is the slotted layout still the right one? (a clustered population spills)
+            f->uploaded = false;
+            CUDA_TRY(cudaStreamSynchronize(f->stream));
+            const uint64_t limit = f->n_read / 4096 > 64 ? f->n_read / 4096 : 64;
+            if (f->layout_pref != 1 && f->h_totals[3] > limit) return demote_to_runs(f);
+        }
+        return FLK_OK;
+    }
     if (int rc = mark()) return rc;
     launch_scan(f->s, m, f->stream);
     if (int rc = mark()) return rc;
@@ -180,6 +343,10 @@ int enqueue_lazy_update(flk_field *f, int bump_step) {
     CUDA_TRY(cudaGetLastError());
     f->n_read = f->w_count;  // single GPU: every WRITE entry is kept
     f->w_count = 0;
+    if (f->uploaded && !f->capturing && f->g.mode == 0) {
+        f->uploaded = false;
+        return maybe_promote_to_slots(f);
+    }
     return FLK_OK;
 }
 
@@ -202,11 +369,55 @@ int enqueue_step(flk_field *f, uint64_t step, int use_step_dev, uint64_t seed, c
         f->prof_events.push_back(e0); f->prof_events.push_back(e1);
         CUDA_TRY(cudaEventRecord(e0, f->stream));
     }
-    launch_step(f->g, f->p, f->s, a, (uint32_t)f->n_read, f->stream);
+    if (f->layout == 1) launch_slot_step(f->g, f->p, slot_args(f->S), f->s, a, 0, f->g.ncols, slot_col_bound(f), f->stream);
+    else launch_step(f->g, f->p, f->s, a, (uint32_t)f->n_read, f->stream);
     if (prof) CUDA_TRY(cudaEventRecord(f->prof_events.back(), f->stream));
     if (f->n_read) f->launches += 1;
     CUDA_TRY(cudaGetLastError());
     f->w_count += f->n_read;
+    return FLK_OK;
+}
+
+// flk_run on the slotted layout.  The two buffers swap roles every tick, so a captured tick only replays from the same
+// parity: the graph holds TWO ticks (one per parity of the READ buffer, `step_dev` bumped by each), an odd tick left over
+// is launched directly.
+int run_slots(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed) {
+    uint64_t t = 0;
+    if (!f->profile && f->use_graph && n_steps >= 8) {
+        const int par = f->S.rd;
+        if (!f->sgraph_valid[par] || f->sgraph_n[par] != f->n_read || f->sgraph_seed[par] != seed) {
+            if (f->sgraph[par]) { cudaGraphExecDestroy(f->sgraph[par]); f->sgraph[par] = nullptr; }
+            f->sgraph_valid[par] = false;
+            cudaGraph_t graph;
+            const uint64_t launches_before = f->launches;
+            CUDA_TRY(cudaStreamBeginCapture(f->stream, cudaStreamCaptureModeThreadLocal));
+            f->capturing = true;
+            int rc = FLK_OK;
+            for (int k = 0; k < 2 && !rc; ++k) {
+                rc = enqueue_step(f, 0, 1, seed, nullptr, 0);
+                if (!rc) rc = enqueue_lazy_update(f, 1);
+            }
+            f->capturing = false;
+            cudaError_t ce = cudaStreamEndCapture(f->stream, &graph);
+            f->sgraph_launches[par] = f->launches - launches_before;
+            f->launches = launches_before;
+            if (rc) { if (ce == cudaSuccess) cudaGraphDestroy(graph); return rc; }
+            CUDA_TRY(ce);
+            ce = cudaGraphInstantiate(&f->sgraph[par], graph, 0);
+            cudaGraphDestroy(graph);
+            CUDA_TRY(ce);
+            f->sgraph_valid[par] = true; f->sgraph_n[par] = f->n_read; f->sgraph_seed[par] = seed;
+        }
+        CUDA_TRY(cudaMemcpyAsync(f->s.step_dev, &first_step, 8, cudaMemcpyHostToDevice, f->stream));
+        for (; t + 2 <= n_steps; t += 2) CUDA_TRY(cudaGraphLaunch(f->sgraph[par], f->stream));
+        f->launches += f->sgraph_launches[par] * (t / 2);
+        f->view_valid = false;
+    }
+    for (; t < n_steps; ++t) {
+        int rc = enqueue_step(f, first_step + t, 0, seed, nullptr, 0);
+        if (!rc) rc = enqueue_lazy_update(f, 0);
+        if (rc) return rc;
+    }
     return FLK_OK;
 }
 
@@ -278,6 +489,13 @@ int flk_field_clear(flk_field *f) {
     f->pend_id.clear(); f->pend_loc.clear(); f->pend_ld.clear();
     f->graph_valid = false;
     if (f->dist) dist_reset_counts(f);
+    if (f->slot_capable) {
+        for (int b = 0; b < 2; ++b) CUDA_TRY(cudaMemsetAsync(f->S.cnt[b], 0, ((uint64_t)f->ncell + 1) * 4, f->stream));
+        CUDA_TRY(cudaMemsetAsync(f->S.spill_cnt, 0, 8, f->stream));
+        CUDA_TRY(cudaMemsetAsync(f->S.colcount, 0, (uint64_t)f->g.ncols * 4, f->stream));
+        CUDA_TRY(cudaMemsetAsync(f->S.colchunk, 0, ((uint64_t)f->g.ncols + 1) * 4, f->stream));
+    }
+    f->layout = 0; f->view_valid = false; f->uploaded = false;
     return FLK_OK;
 }
 
@@ -291,6 +509,12 @@ int flk_set_params(flk_field *f, float cohesion, float avoidance, float randomne
     int rc = update_window(f);
     if (rc) { f->p = old; return rc; }
     f->graph_valid = false;
+    f->sgraph_valid[0] = f->sgraph_valid[1] = false;
+    // the slotted step kernel is written for the shipped query (relax, 3x3 window); anything else steps on the sorted runs
+    if (f->layout == 1 && !slots_params_ok(f)) {
+        rc = demote_to_runs(f);
+        if (rc) { f->p = old; return rc; }
+    }
     return FLK_OK;
 }
 
@@ -299,6 +523,7 @@ int flk_set_math_mode(flk_field *f, int mode) {
     if (mode != 0 && mode != 1) return fail(FLK_E_INVALID, "math mode must be 0 (exact) or 1 (fast)");
     f->math_mode = mode;
     f->graph_valid = false;
+    f->sgraph_valid[0] = f->sgraph_valid[1] = false;
     return FLK_OK;
 }
 
@@ -383,6 +608,12 @@ int flk_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed) 
     if (f->g.mode != 0) return dist_run(f, first_step, n_steps, seed);
     if (f->w_count != 0) return fail(FLK_E_STATE, "flk_run needs an empty WRITE buffer (call flk_lazy_update first)");
     CUDA_TRY(cudaEventRecord(f->ev0, f->stream));
+    if (f->layout == 1) {
+        rc = run_slots(f, first_step, n_steps, seed);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(f->ev1, f->stream));
+        return FLK_OK;
+    }
     // a captured tick pays off from a handful of replays on; short runs without a cached graph launch directly
     const bool have_graph = f->graph_valid && f->graph_n == f->n_read && f->graph_seed == seed;
     if (f->profile || !f->use_graph || (!have_graph && n_steps < 8)) {
@@ -429,6 +660,7 @@ int flk_num_objects(const flk_field *f, uint64_t *n) {
 static int snapshot_impl(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n, bool sync) {
     CHECK_HANDLE(f);
     if (f->g.mode != 0) { int rc = dist_refresh_counts(f); if (rc) return rc; }
+    if (int rc = ensure_view(f)) return rc;
     const uint64_t nr = f->n_read;
     if (n) *n = nr;
     if (nr) {
@@ -473,10 +705,12 @@ int flk_set_objects_dense(flk_field *f, uint64_t n, uint32_t id0, const float *r
                     (unsigned long long)(f->w_count + n), (unsigned long long)f->cap);
     float4 *d_rec = reinterpret_cast<float4 *>(f->scratch);   // staging (free outside lazy_update; stream order protects it)
     CUDA_TRY(cudaMemcpyAsync(d_rec, rec4, n * 16, cudaMemcpyHostToDevice, f->stream));
-    launch_ingest_dense(f->g, f->s, (uint32_t)n, id0, d_rec, (uint32_t)f->w_count, f->stream);
+    if (f->layout == 1) launch_slot_ingest_dense(f->g, slot_args(f->S), f->s, (uint32_t)n, id0, d_rec, nullptr, f->stream);
+    else launch_ingest_dense(f->g, f->s, (uint32_t)n, id0, d_rec, (uint32_t)f->w_count, f->stream);
     f->launches += 1;
     CUDA_TRY(cudaGetLastError());
     f->w_count += n;
+    f->uploaded = true;
     return FLK_OK;
 }
 
@@ -492,7 +726,8 @@ static int snapshot_dense_impl(flk_field *f, uint32_t id0, uint64_t n, float *re
     uint32_t *d_cnt = dense_counter(f);
     CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, f->stream));
     if (f->n_read != n) CUDA_TRY(cudaMemsetAsync(d_out, 0xFF, n * 16, f->stream));   // ids not in the field read back as NaN
-    launch_gather_dense(f->s, (uint32_t)f->n_read, id0, (uint32_t)n, d_out, d_cnt, f->stream);
+    if (f->layout == 1) launch_slot_gather_dense(slot_args(f->S), f->ncell, id0, (uint32_t)n, d_out, d_cnt, f->stream);
+    else launch_gather_dense(f->s, (uint32_t)f->n_read, id0, (uint32_t)n, d_out, d_cnt, f->stream);
     f->launches += f->n_read ? 1 : 0;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(rec4, d_out, n * 16, cudaMemcpyDeviceToHost, f->stream));
@@ -522,6 +757,7 @@ int flk_frame_begin(flk_field *f, uint32_t *id, float *rec4, uint64_t *n) {
         CUDA_TRY(cudaEventCreateWithFlags(&f->ev_frame_ready, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&f->ev_frame_done, cudaEventDisableTiming));
     }
+    if (int rc = ensure_view(f)) return rc;
     const uint64_t nr = f->n_read;
     if (n) *n = nr;
     // the previous frame may still be on its way to the host: do not overwrite the copy it is reading
@@ -553,6 +789,7 @@ int flk_get_object(flk_field *f, uint32_t id, float out[4], int32_t *found) {
     CHECK_HANDLE(f);
     if (!out || !found) return fail(FLK_E_INVALID, "null argument");
     *found = 0;
+    if (int rc = ensure_view(f)) return rc;
     // result slot at the tail of the scratch block (free outside lazy_update; stream order protects it)
     float4 *d_out = reinterpret_cast<float4 *>(f->scratch + ((f->cap * 20 + 15) & ~(uint64_t)15));
     uint32_t *d_found = reinterpret_cast<uint32_t *>(d_out + 1);
@@ -572,6 +809,7 @@ int flk_get_object(flk_field *f, uint32_t id, float out[4], int32_t *found) {
 int flk_get_binning(flk_field *f, uint32_t *cell_start, uint32_t *sorted_ids) {
     CHECK_HANDLE(f);
     if (f->g.mode != 0) { int rc = dist_refresh_counts(f); if (rc) return rc; }
+    if (int rc = ensure_view(f)) return rc;
     if (cell_start)
         CUDA_TRY(cudaMemcpyAsync(cell_start, f->s.cell_start, ((uint64_t)f->ncell + 1) * 4, cudaMemcpyDeviceToHost, f->stream));
     if (sorted_ids && f->n_read)
@@ -587,6 +825,7 @@ int flk_query_batch(flk_field *f, uint64_t nq, const float *loc, float dist, int
     if (nq > 0x7fffffffull) return fail(FLK_E_INVALID, "too many queries");
     offsets[0] = 0;
     if (nq == 0) return FLK_OK;
+    if (int rc0 = ensure_view(f)) return rc0;
     if (dist > 0.0f) {
         const int k = (int)std::floor(dist / f->g.d);
         if (f->g.toroidal && (2 * k + 1 > f->g.mx || 2 * k + 1 > f->g.my))
@@ -751,6 +990,44 @@ int flk_selftest_div2(int device, uint64_t n, uint64_t seed, uint64_t *mismatche
     cudaFree(d);
     if (e != cudaSuccess) return fail(FLK_E_CUDA, "selftest: %s", cudaGetErrorString(e));
     *mismatches = h;
+    return FLK_OK;
+}
+
+int flk_set_layout(flk_field *f, int layout) {
+    CHECK_HANDLE(f);
+    if (layout < -1 || layout > 1) return fail(FLK_E_INVALID, "layout must be -1 (automatic), 0 (sorted runs) or 1 (slots)");
+    if (layout == 1 && !f->slot_capable)
+        return fail(FLK_E_UNSUPPORTED, "this handle cannot use the slotted layout (tiles, non-toroidal field, payload, or a "
+                                       "capacity above half the slots of its cells)");
+    f->layout_pref = layout;
+    if (layout == 0 && f->layout == 1) return demote_to_runs(f);
+    if (layout == 1 && f->layout == 0 && f->w_count == 0 && f->g.mode == 0) return maybe_promote_to_slots(f);
+    return FLK_OK;
+}
+
+int flk_get_layout(flk_field *f, int32_t *layout, int32_t *slots_per_cell, uint32_t totals[4]) {
+    CHECK_HANDLE(f);
+    if (layout) *layout = f->layout;
+    if (slots_per_cell) *slots_per_cell = f->slot_capable ? f->S.C : 0;
+    if (totals) {
+        totals[0] = totals[1] = totals[2] = totals[3] = 0;
+        if (f->layout == 1) {
+            CUDA_TRY(cudaMemcpyAsync(f->h_totals, f->S.totals, 16, cudaMemcpyDeviceToHost, f->stream));
+            CUDA_TRY(cudaStreamSynchronize(f->stream));
+            memcpy(totals, f->h_totals, 16);
+        }
+    }
+    return FLK_OK;
+}
+
+int flk_debug_counters(flk_field *f, uint32_t out[16]) {
+    CHECK_HANDLE(f);
+    if (!out) return fail(FLK_E_INVALID, "out is null");
+    memset(out, 0, 64);
+    if (!f->slot_capable) return FLK_OK;
+    CUDA_TRY(cudaStreamSynchronize(f->stream));
+    CUDA_TRY(cudaMemcpy(out, f->S.dbg, 64, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(f->S.dbg, 0, 64));
     return FLK_OK;
 }
 

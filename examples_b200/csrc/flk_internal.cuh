@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "flk_kernels.cuh"
+#include "flk_slots.cuh"
 
 struct flk_dist_state;  // flk_dist.cu
 
@@ -46,6 +47,18 @@ struct flk_field {
     std::vector<cudaEvent_t> prof_events;      // pairs around every k_step launch (set)
     std::vector<cudaEvent_t> prof_rebin;       // quadruples per lazy_update: start, after scan, after scatter, after rank
     flk_dist_state *dist = nullptr;
+    // fixed-capacity-cell layout (flk_slots.cuh).  layout: 0 = sorted runs (rec / ids / cell_start), 1 = slots.
+    flk::SlotStore S{};
+    int layout = 0;
+    bool slot_capable = false;     // geometry / payload / capacity allow the slotted layout (arrays allocated)
+    int layout_pref = -1;          // -1 automatic, 0 force sorted runs, 1 force slots (flk_set_layout / FLK_LAYOUT)
+    bool view_valid = false;       // layout 1: rec / ids / cell_start hold the READ buffer too (read-side calls)
+    bool uploaded = false;         // objects were uploaded since the last lazy_update (layout decision is due)
+    uint32_t *h_totals = nullptr;  // pinned: {birds, largest column, largest cell, spilled} of a recent READ buffer
+    uint32_t *d_stats = nullptr;   // 2 words: cell statistics of the sorted-runs READ buffer
+    cudaGraphExec_t sgraph[2] = {nullptr, nullptr};   // layout 1: two ticks, first one reading buffer 0 / 1
+    bool sgraph_valid[2] = {false, false};
+    uint64_t sgraph_n[2] = {0, 0}, sgraph_seed[2] = {0, 0}, sgraph_launches[2] = {0, 0};
 };
 
 namespace flk {
@@ -83,5 +96,14 @@ int dist_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed)
 int dist_refresh_counts(flk_field *f);
 void dist_reset_counts(flk_field *f);
 int report_device_errors(flk_field *f, uint32_t flag);
+// layout management (flk_api.cu)
+int slots_alloc(flk_field *f);
+bool slots_params_ok(const flk_field *f);
+int slots_publish(flk_field *f, int bump_step);
+uint32_t slot_col_bound(const flk_field *f);
+int ensure_view(flk_field *f);
+int demote_to_runs(flk_field *f);
+int maybe_promote_to_slots(flk_field *f);
+int run_slots(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed);
 
 }  // namespace flk

@@ -106,6 +106,17 @@ class Field2D:
     def clear(self):
         check(self._L.flk_field_clear(self._h))
 
+    def set_layout(self, layout: int):
+        """-1 automatic, 0 sorted runs, 1 fixed-capacity cell slots (include/flk.h: flk_set_layout)"""
+        check(self._L.flk_set_layout(self._h, layout))
+
+    def layout(self):
+        """(layout in use, slots per cell, [objects, largest column, largest cell, spilled objects])"""
+        lay, c = C.c_int32(), C.c_int32()
+        tot = (C.c_uint32 * 4)()
+        check(self._L.flk_get_layout(self._h, C.byref(lay), C.byref(c), tot))
+        return lay.value, c.value, list(tot)
+
     # ---- write side
     def set_object_location(self, bird: Bird, loc: Real2D):
         check(self._L.flk_set_object_location(self._h, bird.id, loc.x, loc.y, bird.last_d.x, bird.last_d.y))
