@@ -30,7 +30,6 @@ SIGNATURES = {
     "flk_field_dims": [_vp, _P(_i32), _P(_i32), _P(_i32), _P(_i32)],
     "flk_set_layout": [_vp, C.c_int],
     "flk_get_layout": [_vp, _P(_i32), _P(_i32), _P(_u32)],
-    "flk_debug_counters": [_vp, _P(_u32)],
     "flk_set_object_location": [_vp, _u32, _f32, _f32, _f32, _f32],
     "flk_set_objects": [_vp, _u64, _vp, _vp, _vp],
     "flk_set_objects_ex": [_vp, _u64, _vp, _vp, _vp, _vp],

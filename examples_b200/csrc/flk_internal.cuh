@@ -51,11 +51,13 @@ struct flk_field {
     flk::SlotStore S{};
     int layout = 0;
     bool slot_capable = false;     // geometry / payload / capacity allow the slotted layout (arrays allocated)
-    int layout_pref = -1;          // -1 automatic, 0 force sorted runs, 1 force slots (flk_set_layout / FLK_LAYOUT)
+    int layout_pref = -1;          // -1 automatic, 0 classic, 1 slots, 2 slot-staged WRITE buffer (flk_set_layout / FLK_LAYOUT)
+    bool layout_forced = false;    // FLK_LAYOUT: keep the requested form whatever the spill count says (tests)
     bool view_valid = false;       // layout 1: rec / ids / cell_start hold the READ buffer too (read-side calls)
     bool uploaded = false;         // objects were uploaded since the last lazy_update (layout decision is due)
     uint32_t *h_totals = nullptr;  // pinned: {birds, largest column, largest cell, spilled} of a recent READ buffer
     uint32_t *d_stats = nullptr;   // 2 words: cell statistics of the sorted-runs READ buffer
+    uint32_t *h_sw = nullptr;      // pinned: {largest cell, spilled arrivals} of a recent slot-staged lazy_update
     cudaGraphExec_t sgraph[2] = {nullptr, nullptr};   // layout 1: two ticks, first one reading buffer 0 / 1
     bool sgraph_valid[2] = {false, false};
     uint64_t sgraph_n[2] = {0, 0}, sgraph_seed[2] = {0, 0}, sgraph_launches[2] = {0, 0};
@@ -104,6 +106,8 @@ uint32_t slot_col_bound(const flk_field *f);
 int ensure_view(flk_field *f);
 int demote_to_runs(flk_field *f);
 int maybe_promote_to_slots(flk_field *f);
+int decide_write_mode(flk_field *f);
+int set_slotw(flk_field *f, int on);
 int run_slots(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed);
 
 }  // namespace flk

@@ -180,6 +180,33 @@ __device__ __forceinline__ void accumulate_interior(const Geom &g, const Store &
 // the two columns next to a strip boundary is also appended to the message for that neighbour (it is either a
 // migrant or next tick's ghost there); one landing outside the local columns is not kept here.
 // ------------------------------------------------------------------------------------------------
+// one WRITE entry: arrival `slot` of cell `key` (KEY_INVALID: not kept on this GPU), WRITE index w
+__device__ __forceinline__ void write_entry(const Store &s, uint32_t w, uint32_t key, uint32_t slot, const float4 &r,
+                                            uint32_t id) {
+    if (s.slotw) {   // slot-staged: the record goes straight to its cell
+        if (key == KEY_INVALID) return;
+        if (slot < (uint32_t)s.sw_C) {
+            const size_t q = (size_t)key * (uint32_t)s.sw_C + slot;
+            s.sw_rec[q] = r;
+            s.sw_id[q] = id;
+        } else {
+            const uint32_t k = atomicAdd(s.sw_spill_cnt, 1u);
+            if (k < s.sw_spill_cap) {
+                SpillEntry e;
+                e.rec = r; e.id = id; e.cell = key; e.pad0 = 0; e.pad1 = 0;
+                s.sw_spill[k] = e;
+            } else {
+                atomicOr(s.err_flag, ERR_CAPACITY);
+            }
+        }
+        return;
+    }
+    reinterpret_cast<float4 *>(s.trec)[w] = r;
+    s.tid[w] = id;
+    s.tkey[w] = key;
+    s.tslot[w] = slot;
+}
+
 template <bool NOPAY = false, int ROWS = -1>   // ROWS: 0 = rows not split (compiled out), 1 = split, -1 = decided at run time
 __device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, const Rec &out, uint32_t id, uint32_t w,
                                                bool d_ok, const Recip &Rd, uint32_t src) {
@@ -197,10 +224,7 @@ __device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, co
         key = (uint32_t)nlc * (uint32_t)g.dh + (uint32_t)nlr;
         slot = atomicAdd(s.cnt + key, 1u);
     }
-    reinterpret_cast<float4 *>(s.trec)[w] = make_float4(out.x, out.y, out.ldx, out.ldy);
-    s.tid[w] = id;
-    s.tkey[w] = key;
-    s.tslot[w] = slot;
+    write_entry(s, w, key, slot, make_float4(out.x, out.y, out.ldx, out.ldy), id);
     if (g.mode != 0) {
         if (nlc == 0 || nlc == 1) xbuf_append(s, s.sendL, out, id);
         if (nlc == g.nown || nlc == g.nown + 1 || (nlc == FLK_DROP && ncx >= g.mx)) xbuf_append(s, s.sendR, out, id);
@@ -375,7 +399,7 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
         const int lr = TILES ? local_row(g, cell_coord(me.y, g.d, g.dhg)) : 1;
         if (lc == 0 || lc == g.nown + 1 || (TILES && (lr == 0 || lr == g.rown + 1))) {
             // ghost copy (flockers_mpi: received_neighbors): stepped by its owner, dropped here
-            s.tkey[w] = KEY_INVALID;
+            if (!s.slotw) s.tkey[w] = KEY_INVALID;
             return;
         }
         if (TILES && a.skip_bands && (lr <= 2 || lr >= g.rown - 1)) return;   // stepped by k_step_bands (slack row too)
@@ -470,10 +494,7 @@ __global__ void __launch_bounds__(256) k_ingest(const Geom g, const Store s, uin
         key = (uint32_t)lc * (uint32_t)g.dh + (uint32_t)cy;
         slot = atomicAdd(s.cnt + key, 1u);
     }
-    reinterpret_cast<float4 *>(s.trec)[base + j] = make_float4(l.x, l.y, d.x, d.y);
-    s.tid[base + j] = id[j];
-    s.tkey[base + j] = key;
-    s.tslot[base + j] = slot;
+    write_entry(s, base + j, key, slot, make_float4(l.x, l.y, d.x, d.y), id[j]);
     for (uint32_t k = 0; k < s.pw; ++k)
         s.tpay[(size_t)(base + j) * s.pw + k] = payload ? payload[(size_t)j * s.pw + k] : 0u;
 }
@@ -495,10 +516,7 @@ __global__ void __launch_bounds__(256) k_ingest_dense(const Geom g, const Store 
     const int cy = cell_coord(r.y, g.d, g.dhg);
     const uint32_t key = (uint32_t)cx * (uint32_t)g.dh + (uint32_t)cy;
     const uint32_t slot = atomicAdd(s.cnt + key, 1u);
-    reinterpret_cast<float4 *>(s.trec)[base + j] = r;
-    s.tid[base + j] = id0 + j;
-    s.tkey[base + j] = key;
-    s.tslot[base + j] = slot;
+    write_entry(s, base + j, key, slot, r, id0 + j);
     for (uint32_t k = 0; k < s.pw; ++k) s.tpay[(size_t)(base + j) * s.pw + k] = 0u;
 }
 
@@ -533,10 +551,7 @@ __global__ void __launch_bounds__(256) k_unpack(const Geom g, const Store s, int
         slot = atomicAdd(s.cnt + key, 1u);
     }
     const uint32_t w = s.cap + (uint32_t)phase * 2u * s.capx + t;
-    reinterpret_cast<float4 *>(s.trec)[w] = r;
-    s.tid[w] = id;
-    s.tkey[w] = key;
-    s.tslot[w] = slot;
+    write_entry(s, w, key, slot, r, id);
     if (g.mode == 2 && phase == 0) {
         // tiles: a bird that came in from the left/right neighbour and sits in one of my border rows is a ghost (or a
         // migrant) of my lower/upper neighbour too, whose columns are mine: forward it (the diagonal hop)
@@ -795,6 +810,117 @@ __global__ void __launch_bounds__(256, FLK_RANK_MINBLOCKS) k_rank(const Store s,
 void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st) {
     const uint32_t nb = n_upper == 0 ? 1 : ((n_upper + 1) / 2 + 255) / 256;
     k_rank<<<nb, 256, 0, st>>>(s, ncell, bump_step);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_compact: slot-staged WRITE buffer -> READ buffer.  Eight lanes per cell, one staged slot (two when a cell of the warp
+// holds more than eight arrivals) per lane: the lane ranks its id among the cell's ids with shuffles and stores its
+// record at cell_start[cell] + rank.  One pass over the records instead of k_scatter + k_rank: the record is read where
+// Bird::step left it and written once, in place.
+// ------------------------------------------------------------------------------------------------
+// a cell with spilled arrivals (rare): one thread merges the slots and the cell's spill entries by (id, source)
+__device__ __noinline__ void compact_spilled_cell(const Store &s, uint32_t cell, uint32_t cs, uint32_t n) {
+    const uint32_t C = (uint32_t)s.sw_C;
+    const size_t base = (size_t)cell * C;
+    const uint32_t nsp = min(*s.sw_spill_cnt, s.sw_spill_cap);
+    long long prev_id = -1;
+    uint32_t prev_src = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        long long best_id = 0x100000000ll;
+        uint32_t best_src = 0xffffffffu;
+        for (uint32_t q = 0; q < C; ++q) {
+            const long long id = s.sw_id[base + q];
+            const bool after = id > prev_id || (id == prev_id && q > prev_src);
+            if (after && (id < best_id || (id == best_id && q < best_src))) { best_id = id; best_src = q; }
+        }
+        for (uint32_t j = 0; j < nsp; ++j) {
+            if (s.sw_spill[j].cell != cell) continue;
+            const long long id = s.sw_spill[j].id;
+            const uint32_t src = C + j;
+            const bool after = id > prev_id || (id == prev_id && src > prev_src);
+            if (after && (id < best_id || (id == best_id && src < best_src))) { best_id = id; best_src = src; }
+        }
+        if (best_src == 0xffffffffu) return;
+        const uint32_t d = cs + k;
+        if (d < s.cap) {
+            reinterpret_cast<float4 *>(s.rec)[d] = best_src < C ? s.sw_rec[base + best_src] : s.sw_spill[best_src - C].rec;
+            s.ids[d] = (uint32_t)best_id;
+        } else {
+            atomicOr(s.err_flag, ERR_CAPACITY);
+        }
+        prev_id = best_id; prev_src = best_src;
+    }
+}
+
+// (__grid_constant__: the out-of-line spill merge takes the store by reference; without it every thread would first copy
+// the whole parameter struct to its stack)
+__global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Store s, uint32_t ncell, int bump_step) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cell = gid >> 3, l8 = gid & 7u;
+    const int lane = threadIdx.x & 31, grp = lane & 24;
+    if (gid == 0) {
+        *s.n_read_dev = min(s.cell_start[ncell], s.cap);
+        if (bump_step) *s.step_dev += 1;
+        s.sw_totals[1] = min(*s.sw_spill_cnt, s.sw_spill_cap);
+    }
+    uint32_t cs = 0, n = 0;
+    if (cell < ncell) {
+        cs = __ldg(s.cell_start + cell);
+        n = __ldg(s.cell_start + cell + 1) - cs;
+    }
+    const uint32_t C = (uint32_t)s.sw_C;
+    const bool spilled = n > C;
+    const uint32_t ns = spilled ? 0u : n;                  // slots this group ranks (a spilled cell is merged by one thread)
+    uint32_t nmax = ns;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    if (nmax) {   // warp-uniform
+        const size_t base = (size_t)cell * C;
+        const bool two = nmax > 8;
+        // a lane without a slot holds the largest id: it never counts as "smaller" for anybody
+        uint32_t id0 = 0xffffffffu, id1 = 0xffffffffu;
+        float4 r0 = make_float4(0, 0, 0, 0), r1 = r0;
+        const bool h0 = l8 < ns, h1 = two && l8 + 8 < ns;
+        if (h0) { id0 = s.sw_id[base + l8]; r0 = s.sw_rec[base + l8]; }
+        if (h1) { id1 = s.sw_id[base + l8 + 8]; r1 = s.sw_rec[base + l8 + 8]; }
+        // rank among the group's first eight slots (equal ids: lower slot first, so the ranks stay a permutation)
+        uint32_t k0 = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t o = __shfl_sync(0xffffffffu, id0, grp | j);
+            k0 += (o < id0 || (o == id0 && (uint32_t)j < l8)) ? 1u : 0u;
+        }
+        if (!h0) k0 = 0;
+        uint32_t k1 = 0;
+        if (two) {   // warp-uniform, rare: a cell of the warp holds more than eight arrivals
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t o0 = __shfl_sync(0xffffffffu, id0, grp | j);   // first set seen by my second slot
+                const uint32_t o1 = __shfl_sync(0xffffffffu, id1, grp | j);   // second set
+                k1 += (o0 < id1 || o0 == id1) ? 1u : 0u;                      // slot j < 8 <= my second slot
+                k0 += (o1 < id0) ? 1u : 0u;                                   // slot j + 8 > my first slot
+                k1 += (o1 < id1 || (o1 == id1 && (uint32_t)j < l8)) ? 1u : 0u;
+            }
+            // (a lane without a slot holds 0xffffffff and sits at a higher slot number than any real one of its group,
+            //  so it is never counted, not even against a real id 0xffffffff)
+        }
+        if (h0) {
+            const uint32_t d = cs + k0;
+            if (d < s.cap) { reinterpret_cast<float4 *>(s.rec)[d] = r0; s.ids[d] = id0; }
+            else atomicOr(s.err_flag, ERR_CAPACITY);
+        }
+        if (h1) {
+            const uint32_t d = cs + k1;
+            if (d < s.cap) { reinterpret_cast<float4 *>(s.rec)[d] = r1; s.ids[d] = id1; }
+            else atomicOr(s.err_flag, ERR_CAPACITY);
+        }
+    }
+    if (spilled && l8 == 0) compact_spilled_cell(s, cell, cs, n);
+}
+
+void launch_compact(const Store &s, uint32_t ncell, int bump_step, cudaStream_t st) {
+    const uint64_t threads = (uint64_t)ncell * 8;
+    k_compact<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(s, ncell, bump_step);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -6,6 +6,12 @@ namespace flk {
 
 constexpr uint32_t KEY_INVALID = 0xFFFFFFFFu;
 
+// an arrival beyond the slots of its cell (slot-staged WRITE buffer / slotted layout): appended to a list
+struct __align__(16) SpillEntry {
+    float4 rec;
+    uint32_t id, cell, pad0, pad1;
+};
+
 // All device arrays of one handle (DESIGN.md §data layout).  READ buffer = (rec, ids, cell_start), sorted by
 // (cell, id).  WRITE buffer = (trec, tid, tkey, tslot) + per-cell counters cnt, in arrival order.
 struct Store {
@@ -33,6 +39,17 @@ struct Store {
     // tiles (mode 2) add the row direction; received birds occupy WRITE slots [cap, cap + nrecv*capx)
     uint8_t *sendD, *sendU, *recvD, *recvU;
     uint32_t nrecv;        // 2 strips, 4 tiles
+    // slot-staged WRITE buffer (slotw != 0): an arrival goes to sw_rec / sw_id [key * sw_C + arrival slot] instead of
+    // trec / tid / tkey / tslot [w], so that lazy_update is scan + ONE pass (k_compact) instead of scan + scatter + rank;
+    // arrivals beyond sw_C slots of a cell are appended to sw_spill (as large as the capacity: nothing is ever dropped)
+    int slotw;
+    int sw_C;
+    float4 *sw_rec;
+    uint32_t *sw_id;
+    SpillEntry *sw_spill;
+    uint32_t *sw_spill_cnt;
+    uint32_t sw_spill_cap;
+    uint32_t *sw_totals;   // [2] of the last k_compact: largest cell, spilled arrivals
 };
 
 constexpr uint32_t ERR_CAPACITY = 1u;   // more objects than `cap` after an exchange
@@ -82,6 +99,8 @@ void launch_step_bands(const Geom &g, const Params &p, const Store &s, const Ste
 void launch_scan(const Store &s, uint32_t ncell_plus1, cudaStream_t st);
 void launch_scatter(const Store &s, uint32_t n_write_extent, int dist, cudaStream_t st);
 void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st);
+// slot-staged WRITE buffer -> READ buffer in (cell, ascending id) order, given cell_start (one pass, 8 lanes per cell)
+void launch_compact(const Store &s, uint32_t ncell, int bump_step, cudaStream_t st);
 void launch_selftest_div2(uint64_t n, uint64_t seed, unsigned long long *mismatches, cudaStream_t st);
 void launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t st);
 void launch_find(const Store &s, uint32_t n_upper, uint32_t id, float4 *out, uint32_t *found, cudaStream_t st);

@@ -14,13 +14,6 @@
 
 namespace flk {
 
-#ifdef FLK_SLOT_DEBUG
-#define DBG(S, i) do { if (threadIdx.x == 0) atomicAdd((S).dbg + (i), 1u); } while (0)
-#define DBGT(S, i) atomicAdd((S).dbg + (i), 1u)
-#else
-#define DBG(S, i) do { } while (0)
-#define DBGT(S, i) do { } while (0)
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // block-wide exclusive scan of one value per thread (returns the exclusive prefix, the total in *total)
@@ -450,9 +443,8 @@ k_slot_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, co
 void launch_slot_step(const Geom &g, const Params &p, const SlotArgs &S, const Store &s, const StepArgs &a, int col_lo,
                       int col_hi, uint32_t max_col_birds, cudaStream_t st) {
     if (col_hi <= col_lo) return;
-    static const int notile = [] { const char *e = getenv("FLK_SLOT_NOTILE"); return e ? atoi(e) : 0; }();   // A/B runs
     const bool fast = p.relax && g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && g.d >= 0x1p-20f && g.d <= 4096.0f &&
-                      !a.identity && p.radius > 0.0f && !notile;
+                      !a.identity && p.radius > 0.0f;
     // blockIdx.x = 0: the column's seam cells; 1 + m: chunk m.  max_col_birds bounds the largest column loosely (the last
     // CTA of a column loops over whatever the bound misses)
     uint32_t chunks = (max_col_birds + SLOT_CHUNK - 1) / SLOT_CHUNK;
@@ -694,7 +686,8 @@ void launch_slot_unpack(const Geom &g, const SlotArgs &S, const Store &s, cudaSt
 // ------------------------------------------------------------------------------------------------
 // read side
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_slot_materialize(const Geom g, const SlotArgs S, const Store s, uint32_t ncell) {
+__global__ void __launch_bounds__(256) k_slot_materialize(const __grid_constant__ Geom g, const __grid_constant__ SlotArgs S,
+                                                          const __grid_constant__ Store s, uint32_t ncell) {
     const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell == 0) *s.n_read_dev = min(s.cell_start[ncell], s.cap);
     if (cell >= ncell) return;

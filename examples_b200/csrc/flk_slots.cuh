@@ -20,11 +20,6 @@ namespace flk {
 constexpr int SLOT_C_MAX = 16;         // 4-bit slot numbers in perm
 constexpr int SLOT_CHUNK = 128;        // birds per CTA of the slotted step kernel (= FLK_STEP_BS)
 
-struct __align__(16) SpillEntry {
-    float4 rec;
-    uint32_t id, cell, pad0, pad1;
-};
-
 // the slotted store of one handle (both buffers)
 struct SlotStore {
     float4 *rec[2] = {nullptr, nullptr};
@@ -39,7 +34,6 @@ struct SlotStore {
     uint32_t *coltab = nullptr;        // [ncols*stride] chunk m of column c starts at row (lo 16 bits), `off` birds into it
     uint32_t *totals = nullptr;        // [4] READ buffer: birds, largest column, largest cell, spilled birds
     uint32_t *ticket = nullptr;        // last-block-done counter of k_slot_colscan
-    uint32_t *dbg = nullptr;           // [16] debug counters (FLK_SLOT_DEBUG builds)
     uint32_t stride = 0;
     uint32_t spill_cap = 0;
     int C = 0;
@@ -65,7 +59,6 @@ struct SlotArgs {
     uint32_t stride;
     uint32_t spill_cap;
     int C;
-    uint32_t *dbg;
 };
 
 inline SlotArgs slot_args(const SlotStore &S) {
@@ -76,7 +69,7 @@ inline SlotArgs slot_args(const SlotStore &S) {
     a.rspill = S.spill[r]; a.rspill_cnt = S.spill_cnt + r;
     a.wrec = S.rec[w]; a.wid = S.id[w]; a.wcnt = S.cnt[w];
     a.wspill = S.spill[w]; a.wspill_cnt = S.spill_cnt + w;
-    a.stride = S.stride; a.spill_cap = S.spill_cap; a.C = S.C; a.dbg = S.dbg;
+    a.stride = S.stride; a.spill_cap = S.spill_cap; a.C = S.C;
     return a;
 }
 

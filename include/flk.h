@@ -78,14 +78,19 @@ int flk_set_params(flk_field *f, float cohesion, float avoidance, float randomne
  * 1 = fast: reciprocal-based division in the neighbour loop (<= 2 ulp per term, same order). */
 int flk_set_math_mode(flk_field *f, int mode);
 
-/* Storage layout of the double buffer.  0 = sorted runs: READ is one array sorted by (cell, id), lazy_update
- * is a counting sort (scan, scatter, rank).  1 = slots: every cell owns a fixed number of record slots, Bird::step stores
- * each successor straight into its cell of the next READ buffer and lazy_update is one pass over the cell counters.
- * Both produce the same results bit for bit.  -1 (default) = automatic: slots for single-GPU and strip handles on a toroidal
- * field with the shipped query (relax, 3x3 window) while at most a handful of birds overflow their cell's slots, sorted
- * runs otherwise (clustered flocks, tiles, payloads, other windows); the switch happens inside flk_lazy_update /
- * flk_set_params / flk_synchronize.  flk_get_layout reports the layout in use, the slots per cell and, for layout 1,
- * {objects, largest column, largest cell, objects beyond their cell's slots} of the READ buffer. */
+/* Storage layout of the double buffer.  All forms produce the same results bit for bit.
+ *   0  sorted runs, classic WRITE buffer: READ is one array sorted by (cell, id); Bird::step appends successors in arrival
+ *      order and lazy_update is a counting sort (scan, scatter, rank).  Any density, any handle.
+ *   2  sorted runs, slot-staged WRITE buffer: Bird::step stores each successor straight into one of a fixed number of
+ *      slots of its cell and lazy_update is scan + ONE pass that ranks and compacts every cell.  Single-GPU handles
+ *      without payload; arrivals beyond a cell's slots go to a spill list (nothing is dropped).
+ *   1  slots as the READ buffer too (fixed-capacity cells read by the step kernel directly): kept as a measured
+ *      alternative, slower on B200, toroidal fields with the shipped query only.
+ *  -1  (default) automatic = form 0: on B200 form 2 measured within 2 % of it and form 1 slower; forms 1
+ *      and 2 are entered on request only, when the next upload is published, and left again (for form 0) when the spill
+ *      count of a tick exceeds a handful of birds (forms requested through the environment are kept regardless).
+ * flk_get_layout reports the form in use, the slots per cell and {objects, largest column (form 1), largest cell, objects
+ * beyond their cell's slots} of the last lazy_update. */
 int flk_set_layout(flk_field *f, int layout);
 int flk_get_layout(flk_field *f, int32_t *layout, int32_t *slots_per_cell, uint32_t totals[4]);
 
@@ -197,10 +202,6 @@ int flk_use_graph(flk_field *f, int on);
 int flk_profile_step_kernel(flk_field *f, double *total_ms, uint64_t *launches);
 /* total device time (ms) of the three lazy_update phases {scan, scatter, rank} and the number of lazy_updates timed */
 int flk_profile_rebin(flk_field *f, double ms[3], uint64_t *updates);
-
-/* diagnostics: counters of the slotted step kernel (all zero unless the library was built with -DFLK_SLOT_DEBUG):
- * CTAs, tile-path CTAs, general-path CTAs, ...; reading clears them */
-int flk_debug_counters(flk_field *f, uint32_t out[16]);
 
 /* pinned host memory helpers (fast flk_set_objects / flk_snapshot) */
 int flk_host_alloc(void **p, uint64_t bytes);

@@ -17,4 +17,7 @@ f.lazy_update()
 f.use_graph(False)
 f.run(0, 14)
 f.synchronize()
-print("layout", f.layout(), "ms/tick", f.elapsed_ms() / 14)
+f.profile_enable(2)
+f.run(14, 10)
+f.synchronize()
+print("layout", f.layout()[0], "rebin", [round(x, 4) for x in f.profile_rebin()], "k_step", f.profile_step_kernel()[0] / 10)
