@@ -40,6 +40,9 @@ SIGNATURES = {
     "flk_get_neighbors_within_relax_distance": [_vp, _f32, _f32, _f32, _vp, _u32, _P(_u32)],
     "flk_get_neighbors_within_distance": [_vp, _f32, _f32, _f32, _vp, _u32, _P(_u32)],
     "flk_query_batch": [_vp, _u64, _vp, _f32, C.c_int, _vp, _vp, _u64],
+    "flk_query_batch_objects": [_vp, _u64, _vp, _f32, C.c_int, _vp, _vp, _u64],
+    "flk_get_neighbors_within_relax_distance_objects": [_vp, _f32, _f32, _f32, _vp, _u32, _P(_u32)],
+    "flk_get_neighbors_within_distance_objects": [_vp, _f32, _f32, _f32, _vp, _u32, _P(_u32)],
     "flk_num_objects": [_vp, _P(_u64)],
     "flk_snapshot": [_vp, _vp, _vp, _vp, _P(_u64)],
     "flk_snapshot_async": [_vp, _vp, _vp, _vp, _P(_u64)],
@@ -78,6 +81,9 @@ SIGNATURES = {
     "flk_dist_create_tiles": [_f32, _f32, _f32, _u64, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _P(_vp)],
     "flk_mgpu_create_tiles": [_f32, _f32, _f32, _u64, C.c_int, _P(C.c_int), C.c_int, _vp, _vp, _P(_vp)],
     "flk_dist_tile": [_vp, _P(_i32), _P(_i32), _P(_i32), _P(_i32)],
+    "flk_dist_create_ex": [_f32, _f32, _f32, _u64, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _u32, _P(_vp)],
+    "flk_mgpu_create_ex": [_f32, _f32, _f32, _u64, C.c_int, _P(C.c_int), C.c_int, _vp, _vp, _u32, _P(_vp)],
+    "flk_dist_snapshot_owned_ex": [_vp, _vp, _vp, _vp, _vp, _P(_u64)],
     "flk_balance_columns": [_vp, _u64, _u64, _f32, _f32, C.c_int, _vp],
     "flk_mgpu_commit": [_P(_vp), C.c_int],
     "flk_mgpu_step": [_P(_vp), C.c_int, _u64, _u64, _vp, _u64],

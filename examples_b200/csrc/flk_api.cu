@@ -626,9 +626,9 @@ int flk_set_objects_ex(flk_field *f, uint64_t n, const uint32_t *id, const float
                        const void *payload) {
     CHECK_HANDLE(f);
     if (n && (!id || !loc || !last_d)) return fail(FLK_E_INVALID, "null array");
-    if (f->g.mode != 0) return fail(FLK_E_UNSUPPORTED, "payloads are not carried by strip handles");
     int rc = flush_pending(f);
     if (rc) return rc;
+    if (f->g.mode != 0) return dist_set_objects(f, n, id, loc, last_d, static_cast<const uint32_t *>(payload));
     return write_append(f, n, id, loc, last_d, static_cast<const uint32_t *>(payload));
 }
 
@@ -887,9 +887,25 @@ int flk_get_binning(flk_field *f, uint32_t *cell_start, uint32_t *sorted_ids) {
     return FLK_OK;
 }
 
+static int query_batch_impl(flk_field *f, uint64_t nq, const float *loc, float dist, int relax, uint64_t *offsets,
+                            uint32_t *ids, uint64_t cap, int objects);
+
 int flk_query_batch(flk_field *f, uint64_t nq, const float *loc, float dist, int relax, uint64_t *offsets,
                     uint32_t *ids, uint64_t cap) {
+    return query_batch_impl(f, nq, loc, dist, relax, offsets, ids, cap, 0);
+}
+
+int flk_query_batch_objects(flk_field *f, uint64_t nq, const float *loc, float dist, int relax, uint64_t *offsets,
+                            flk_bird *objects, uint64_t cap) {
+    static_assert(sizeof(flk_bird) == 20, "flk_bird is Bird's 20-byte wire form");
+    return query_batch_impl(f, nq, loc, dist, relax, offsets, reinterpret_cast<uint32_t *>(objects), cap, 1);
+}
+
+// `ids` receives ids (objects = 0) or 5-word objects (objects = 1); cap counts entries, not words
+static int query_batch_impl(flk_field *f, uint64_t nq, const float *loc, float dist, int relax, uint64_t *offsets,
+                            uint32_t *ids, uint64_t cap, int objects) {
     CHECK_HANDLE(f);
+    const uint64_t words = objects ? 5 : 1;
     if (!offsets || (nq && !loc)) return fail(FLK_E_INVALID, "null array");
     if (nq > 0x7fffffffull) return fail(FLK_E_INVALID, "too many queries");
     offsets[0] = 0;
@@ -922,12 +938,12 @@ int flk_query_batch(flk_field *f, uint64_t nq, const float *loc, float dist, int
         goto done;
     }
     if (offsets[nq]) {
-        Q_TRY(cudaMalloc(&d_out, offsets[nq] * 4));
+        Q_TRY(cudaMalloc(&d_out, offsets[nq] * 4 * words));
         Q_TRY(cudaMemcpyAsync(d_off, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, f->stream));
-        launch_query_fill(f->g, f->s, (uint32_t)nq, d_loc, dist, relax, d_off, d_out, f->stream);
+        launch_query_fill(f->g, f->s, (uint32_t)nq, d_loc, dist, relax, d_off, d_out, f->stream, objects);
         f->launches += 1;
         Q_TRY(cudaGetLastError());
-        Q_TRY(cudaMemcpyAsync(ids, d_out, offsets[nq] * 4, cudaMemcpyDeviceToHost, f->stream));
+        Q_TRY(cudaMemcpyAsync(ids, d_out, offsets[nq] * 4 * words, cudaMemcpyDeviceToHost, f->stream));
         Q_TRY(cudaStreamSynchronize(f->stream));
     }
 done:
@@ -936,22 +952,34 @@ done:
     return rc;
 }
 
-static int query_one(flk_field *f, float x, float y, float dist, int relax, uint32_t *ids, uint32_t cap, uint32_t *n) {
+static int query_one(flk_field *f, float x, float y, float dist, int relax, uint32_t *ids, uint32_t cap, uint32_t *n,
+                     int objects = 0) {
     CHECK_HANDLE(f);
     if (!n) return fail(FLK_E_INVALID, "n is null");
     const float loc[2] = {x, y};
     uint64_t off[2] = {0, 0};
-    // first try with the caller's buffer; on overflow report the full size with the first `cap` ids
-    int rc = flk_query_batch(f, 1, loc, dist, relax, off, ids, cap);
+    const size_t words = objects ? 5 : 1;
+    // first try with the caller's buffer; on overflow report the full size with the first `cap` entries
+    int rc = query_batch_impl(f, 1, loc, dist, relax, off, ids, cap, objects);
     *n = (uint32_t)off[1];
     if (rc == FLK_E_CAPACITY && off[1] > cap) {
-        std::vector<uint32_t> tmp(off[1]);
-        int rc2 = flk_query_batch(f, 1, loc, dist, relax, off, tmp.data(), tmp.size());
+        std::vector<uint32_t> tmp(off[1] * words);
+        int rc2 = query_batch_impl(f, 1, loc, dist, relax, off, tmp.data(), off[1], objects);
         if (rc2) return rc2;
-        if (ids && cap) memcpy(ids, tmp.data(), (size_t)cap * 4);
-        return fail(FLK_E_CAPACITY, "query result has %u ids, buffer holds %u", *n, cap);
+        if (ids && cap) memcpy(ids, tmp.data(), (size_t)cap * 4 * words);
+        return fail(FLK_E_CAPACITY, "query result has %u entries, buffer holds %u", *n, cap);
     }
     return rc;
+}
+
+int flk_get_neighbors_within_relax_distance_objects(flk_field *f, float x, float y, float dist, flk_bird *objects,
+                                                    uint32_t cap, uint32_t *n) {
+    return query_one(f, x, y, dist, 1, reinterpret_cast<uint32_t *>(objects), cap, n, 1);
+}
+
+int flk_get_neighbors_within_distance_objects(flk_field *f, float x, float y, float dist, flk_bird *objects, uint32_t cap,
+                                              uint32_t *n) {
+    return query_one(f, x, y, dist, 0, reinterpret_cast<uint32_t *>(objects), cap, n, 1);
 }
 
 int flk_get_neighbors_within_relax_distance(flk_field *f, float x, float y, float dist, uint32_t *ids, uint32_t cap,

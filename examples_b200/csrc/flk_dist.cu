@@ -152,8 +152,9 @@ static int make_bounds(int mx, int world, const int32_t *col_bounds, std::vector
 // common part of flk_dist_create / flk_mgpu_create
 static int dist_field_new(float w, float h, float disc, uint64_t capacity, int device, int rank, int world,
                           int transport, flk_field **out, const int32_t *col_bounds = nullptr, int Py = 1,
-                          const int32_t *row_bounds = nullptr) {
+                          const int32_t *row_bounds = nullptr, uint32_t payload_bytes = 0) {
     *out = nullptr;
+    if (payload_bytes % 4 != 0 || payload_bytes > 256) return fail(FLK_E_INVALID, "payload_bytes must be a multiple of 4, <= 256");
     if (world < 2) return fail(FLK_E_INVALID, "strip decomposition needs world >= 2 (use flk_field_create for one GPU)");
     if (rank < 0 || rank >= world) return fail(FLK_E_INVALID, "rank %d out of range", rank);
     if (capacity == 0 || capacity > 0x7fffffffull) return fail(FLK_E_INVALID, "capacity must be in [1, 2^31)");
@@ -198,6 +199,7 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     uint64_t capx = 8 * (capacity / (uint64_t)narrowest) + 4096;
     if (capx > capacity) capx = capacity;
     f->s.capx = (uint32_t)capx;
+    f->s.pw = payload_bytes / 4;      // Field2D<O>: the payload words travel in the halo / migration messages too
     rc = [&]() -> int {
         CUDA_TRY(cudaSetDevice(device));
         CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
@@ -216,7 +218,7 @@ static int dist_field_new(float w, float h, float disc, uint64_t capacity, int d
     d->right = py * Px + (px + 1) % Px;
     d->down = ((py + Py - 1) % Py) * Px + px;
     d->up = ((py + 1) % Py) * Px + px;
-    const size_t xb = (xbuf_bytes(f->s.capx) + 255) & ~(size_t)255;
+    const size_t xb = (xbuf_bytes(f->s.capx, f->s.pw) + 255) & ~(size_t)255;
     const int nbuf = Py > 1 ? 8 : 4;
     cudaError_t e = cudaMalloc(&d->xbuf, nbuf * xb);
     if (e == cudaSuccess) e = cudaMemsetAsync(d->xbuf, 0, nbuf * xb, f->stream);
@@ -335,7 +337,7 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
 // phase 2: move the messages (on the comm stream, as soon as the border columns are done)
 static int dist_phase_exchange(flk_field *f) {
     flk_dist_state *d = f->dist;
-    const size_t nbytes = xbuf_bytes(f->s.capx);
+    const size_t nbytes = xbuf_bytes(f->s.capx, f->s.pw);
     cudaStream_t cs = d->comm_stream;
     // my own border step of THIS tick is behind my unpack/scatter of the previous tick on the main stream, so waiting
     // for it also protects the receive buffers the previous tick may still be reading
@@ -376,7 +378,7 @@ static int dist_phase_unpack_x(flk_field *f) {
 // tiles, phase 2c: the row-direction exchange
 static int dist_phase_exchange_y(flk_field *f) {
     flk_dist_state *d = f->dist;
-    const size_t nbytes = xbuf_bytes(f->s.capx);
+    const size_t nbytes = xbuf_bytes(f->s.capx, f->s.pw);
     cudaStream_t cs = d->comm_stream;
     CUDA_TRY(cudaStreamWaitEvent(cs, d->ev_fwd, 0));
     if (d->transport == 0) {
@@ -468,9 +470,9 @@ void dist_reset_counts(flk_field *f) {
     d->known = 0; d->known_tick = 0; d->copy_tick = 0; d->tick_no = 0;
 }
 
-int dist_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld) {
+int dist_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld, const uint32_t *payload) {
     dist_reset_counts(f);
-    return write_append(f, n, id, loc, ld);
+    return write_append(f, n, id, loc, ld, payload);
 }
 
 static int dist_check_errors(flk_field *f) {
@@ -533,11 +535,18 @@ int flk_dist_create_cols(float width, float height, float discretization, uint64
 int flk_dist_create_tiles(float width, float height, float discretization, uint64_t capacity, int device, int rank,
                           int world, const uint8_t *id128, int tile_rows, const int32_t *col_bounds,
                           const int32_t *row_bounds, flk_field **out) {
+    return flk_dist_create_ex(width, height, discretization, capacity, device, rank, world, id128, tile_rows, col_bounds,
+                              row_bounds, 0, out);
+}
+
+int flk_dist_create_ex(float width, float height, float discretization, uint64_t capacity, int device, int rank,
+                       int world, const uint8_t *id128, int tile_rows, const int32_t *col_bounds,
+                       const int32_t *row_bounds, uint32_t payload_bytes, flk_field **out) {
     if (!out || !id128) return fail(FLK_E_INVALID, "null argument");
     int rc = nccl_load();
     if (rc) return rc;
     rc = dist_field_new(width, height, discretization, capacity, device, rank, world, 0, out, col_bounds, tile_rows,
-                        row_bounds);
+                        row_bounds, payload_bytes);
     if (rc) return rc;
     ncclUniqueId id;
     memcpy(id.internal, id128, 128);
@@ -592,11 +601,18 @@ int flk_mgpu_create_cols(float width, float height, float discretization, uint64
 int flk_mgpu_create_tiles(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
                           const int *devices, int tile_rows, const int32_t *col_bounds, const int32_t *row_bounds,
                           flk_field **out) {
+    return flk_mgpu_create_ex(width, height, discretization, capacity_per_rank, n, devices, tile_rows, col_bounds, row_bounds,
+                              0, out);
+}
+
+int flk_mgpu_create_ex(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
+                       const int *devices, int tile_rows, const int32_t *col_bounds, const int32_t *row_bounds,
+                       uint32_t payload_bytes, flk_field **out) {
     if (!out || !devices || n < 2) return fail(FLK_E_INVALID, "need n >= 2 devices");
     flk_field **grp = new flk_field *[n];
     for (int r = 0; r < n; ++r) {
         int rc = dist_field_new(width, height, discretization, capacity_per_rank, devices[r], r, n, 1, &grp[r], col_bounds,
-                                tile_rows, row_bounds);
+                                tile_rows, row_bounds, payload_bytes);
         if (rc) {
             for (int q = 0; q < r; ++q) { grp[q]->dist->group = nullptr; flk_field_destroy(grp[q]); }
             delete[] grp;
@@ -819,11 +835,16 @@ int flk_dist_num_owned(flk_field *f, uint64_t *n) {
 }
 
 // snapshot of the birds this rank OWNS (ghost copies excluded), (cell, id) order
-static int dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n, bool sync) {
+static int dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n, bool sync,
+                               void *payload = nullptr) {
     CHECK_HANDLE(f);
-    if (f->g.mode == 0) return sync ? flk_snapshot(f, id, loc, last_d, n) : flk_snapshot_async(f, id, loc, last_d, n);
+    if (f->g.mode == 0) {
+        if (payload) return flk_snapshot_ex(f, id, loc, last_d, payload, n);
+        return sync ? flk_snapshot(f, id, loc, last_d, n) : flk_snapshot_async(f, id, loc, last_d, n);
+    }
     int rc = dist_check_errors(f);
     if (rc) return rc;
+    if (!f->s.pw) payload = nullptr;
     if (f->g.mode == 2) {   // tiles: compact the owned birds into the scratch block, then copy
         const uint64_t cap = f->cap;
         uint32_t *d_id = reinterpret_cast<uint32_t *>(f->scratch);
@@ -832,13 +853,15 @@ static int dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *la
         uint32_t *d_cnt = reinterpret_cast<uint32_t *>(f->scratch + ((cap * 20 + 15) & ~(uint64_t)15) + 96);
         uint32_t h = 0;
         CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 4, f->stream));
+        // the owned payload rows are compacted into the WRITE payload array (free between ticks)
         launch_compact_owned(f->g, f->s, (uint32_t)cap, id ? d_id : nullptr, loc ? d_loc : nullptr, last_d ? d_ld : nullptr,
-                             d_cnt, f->stream);
+                             d_cnt, f->stream, payload ? f->s.tpay : nullptr);
         f->launches += 1;
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(&h, d_cnt, 4, cudaMemcpyDeviceToHost, f->stream));
         CUDA_TRY(cudaStreamSynchronize(f->stream));
         if (n) *n = h;
+        if (h && payload) CUDA_TRY(cudaMemcpyAsync(payload, f->s.tpay, (uint64_t)h * f->s.pw * 4, cudaMemcpyDeviceToHost, f->stream));
         if (h && id) CUDA_TRY(cudaMemcpyAsync(id, d_id, (uint64_t)h * 4, cudaMemcpyDeviceToHost, f->stream));
         if (h && loc) CUDA_TRY(cudaMemcpyAsync(loc, d_loc, (uint64_t)h * 8, cudaMemcpyDeviceToHost, f->stream));
         if (h && last_d) CUDA_TRY(cudaMemcpyAsync(last_d, d_ld, (uint64_t)h * 8, cudaMemcpyDeviceToHost, f->stream));
@@ -871,6 +894,12 @@ static int dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *la
         if (n0) CUDA_TRY(cudaMemcpyAsync(id, f->s.ids + b[0], n0 * 4, cudaMemcpyDeviceToHost, f->stream));
         if (n1) CUDA_TRY(cudaMemcpyAsync(id + n0, f->s.ids + b[2], n1 * 4, cudaMemcpyDeviceToHost, f->stream));
     }
+    if (payload) {   // payload rows follow the READ order: the same two index ranges
+        const uint64_t row = (uint64_t)f->s.pw * 4;
+        uint8_t *dst = static_cast<uint8_t *>(payload);
+        if (n0) CUDA_TRY(cudaMemcpyAsync(dst, f->s.pay + (uint64_t)b[0] * f->s.pw, n0 * row, cudaMemcpyDeviceToHost, f->stream));
+        if (n1) CUDA_TRY(cudaMemcpyAsync(dst + n0 * row, f->s.pay + (uint64_t)b[2] * f->s.pw, n1 * row, cudaMemcpyDeviceToHost, f->stream));
+    }
     if (sync) CUDA_TRY(cudaStreamSynchronize(f->stream));
     return FLK_OK;
 }
@@ -881,6 +910,10 @@ int flk_dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_
 
 int flk_dist_snapshot_owned_async(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n) {
     return dist_snapshot_owned(f, id, loc, last_d, n, false);
+}
+
+int flk_dist_snapshot_owned_ex(flk_field *f, uint32_t *id, float *loc, float *last_d, void *payload, uint64_t *n) {
+    return dist_snapshot_owned(f, id, loc, last_d, n, true, payload);
 }
 
 }  // extern "C"

@@ -93,7 +93,8 @@ int enqueue_lazy_update(flk_field *f, int bump_step);
 
 // flk_dist.cu
 void dist_free(flk_field *f);
-int dist_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld);
+int dist_set_objects(flk_field *f, uint64_t n, const uint32_t *id, const float *loc, const float *ld,
+                     const uint32_t *payload = nullptr);
 int dist_run(flk_field *f, uint64_t first_step, uint64_t n_steps, uint64_t seed);
 int dist_refresh_counts(flk_field *f);
 void dist_reset_counts(flk_field *f);

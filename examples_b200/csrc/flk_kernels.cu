@@ -225,13 +225,14 @@ __device__ __forceinline__ void emit_successor(const Geom &g, const Store &s, co
         slot = atomicAdd(s.cnt + key, 1u);
     }
     write_entry(s, w, key, slot, make_float4(out.x, out.y, out.ldx, out.ldy), id);
+    const uint32_t *pay = (!NOPAY && s.pw) ? s.pay + (size_t)src * s.pw : nullptr;   // the object's payload travels with it
     if (g.mode != 0) {
-        if (nlc == 0 || nlc == 1) xbuf_append(s, s.sendL, out, id);
-        if (nlc == g.nown || nlc == g.nown + 1 || (nlc == FLK_DROP && ncx >= g.mx)) xbuf_append(s, s.sendR, out, id);
+        if (nlc == 0 || nlc == 1) xbuf_append(s, s.sendL, out, id, pay);
+        if (nlc == g.nown || nlc == g.nown + 1 || (nlc == FLK_DROP && ncx >= g.mx)) xbuf_append(s, s.sendR, out, id, pay);
     }
     if (rows) {   // same rule along y; a corner successor goes into both (and is forwarded diagonally, k_unpack)
-        if (nlr == 0 || nlr == 1) xbuf_append(s, s.sendD, out, id);
-        if (nlr == g.rown || nlr == g.rown + 1 || (nlr == FLK_DROP && ncy >= g.my)) xbuf_append(s, s.sendU, out, id);
+        if (nlr == 0 || nlr == 1) xbuf_append(s, s.sendD, out, id, pay);
+        if (nlr == g.rown || nlr == g.rown + 1 || (nlr == FLK_DROP && ncy >= g.my)) xbuf_append(s, s.sendU, out, id, pay);
     }
 }
 
@@ -552,12 +553,14 @@ __global__ void __launch_bounds__(256) k_unpack(const Geom g, const Store s, int
     }
     const uint32_t w = s.cap + (uint32_t)phase * 2u * s.capx + t;
     write_entry(s, w, key, slot, r, id);
+    const uint32_t *pay = s.pw ? xbuf_pay(buf, s.capx) + (size_t)j * s.pw : nullptr;
+    for (uint32_t k = 0; k < s.pw; ++k) s.tpay[(size_t)w * s.pw + k] = pay[k];
     if (g.mode == 2 && phase == 0) {
         // tiles: a bird that came in from the left/right neighbour and sits in one of my border rows is a ghost (or a
         // migrant) of my lower/upper neighbour too, whose columns are mine: forward it (the diagonal hop)
         const Rec rr = Rec{r.x, r.y, r.z, r.w};
-        if (lr == 0 || lr == 1) xbuf_append(s, s.sendD, rr, id);
-        if (lr == g.rown || lr == g.rown + 1 || (lr == FLK_DROP && cy >= g.my)) xbuf_append(s, s.sendU, rr, id);
+        if (lr == 0 || lr == 1) xbuf_append(s, s.sendD, rr, id, pay);
+        if (lr == g.rown || lr == g.rown + 1 || (lr == FLK_DROP && cy >= g.my)) xbuf_append(s, s.sendU, rr, id, pay);
     }
 }
 
@@ -570,7 +573,7 @@ void launch_unpack(const Geom &g, const Store &s, cudaStream_t st, int phase) {
 // scattered over the READ buffer; append them to the output arrays (order: arrival; callers sort by id)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_compact_owned(const Geom g, const Store s, uint32_t n_upper, uint32_t *out_id,
-                                                       float2 *out_loc, float2 *out_ld, uint32_t *counter) {
+                                                       float2 *out_loc, float2 *out_ld, uint32_t *counter, uint32_t *out_pay) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_upper || i >= *s.n_read_dev) return;
     const float4 r = reinterpret_cast<const float4 *>(s.rec)[i];
@@ -583,12 +586,13 @@ __global__ void __launch_bounds__(256) k_compact_owned(const Geom g, const Store
     if (out_id) out_id[k] = s.ids[i];
     if (out_loc) out_loc[k] = make_float2(r.x, r.y);
     if (out_ld) out_ld[k] = make_float2(r.z, r.w);
+    if (out_pay) for (uint32_t q = 0; q < s.pw; ++q) out_pay[(size_t)k * s.pw + q] = s.pay[(size_t)i * s.pw + q];
 }
 
 void launch_compact_owned(const Geom &g, const Store &s, uint32_t n_upper, uint32_t *out_id, float2 *out_loc, float2 *out_ld,
-                          uint32_t *counter, cudaStream_t st) {
+                          uint32_t *counter, cudaStream_t st, uint32_t *out_pay) {
     if (n_upper == 0) return;
-    k_compact_owned<<<(n_upper + 255) / 256, 256, 0, st>>>(g, s, n_upper, out_id, out_loc, out_ld, counter);
+    k_compact_owned<<<(n_upper + 255) / 256, 256, 0, st>>>(g, s, n_upper, out_id, out_loc, out_ld, counter, out_pay);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1020,7 +1024,8 @@ void launch_gather_dense(const Store &s, uint32_t n_upper, uint32_t id0, uint32_
 // ------------------------------------------------------------------------------------------------
 // queries (Field2D::get_neighbors_within_{relax_,}distance): one thread per query location
 // ------------------------------------------------------------------------------------------------
-template <bool FILL>
+// FILL: 0 = count, 1 = ids, 2 = whole objects {id, loc.x, loc.y, last_d.x, last_d.y} (20 bytes, Bird's wire form)
+template <int FILL>
 __global__ void __launch_bounds__(128) k_query(const Geom g, const Store s, uint32_t nq, const float2 *__restrict__ loc,
                                                float dist, int relax, uint32_t *__restrict__ counts,
                                                const uint64_t *__restrict__ offsets, uint32_t *__restrict__ out) {
@@ -1034,7 +1039,7 @@ __global__ void __launch_bounds__(128) k_query(const Geom g, const Store s, uint
         const int cy = local_row(g, cell_coord(l.y, g.d, g.dhg));   // row of the local cell arrays
         const int lc = local_col(g, gcx);
         const float halfW = __fdiv_rn(g.W, 2.0f), halfH = __fdiv_rn(g.H, 2.0f);
-        uint32_t *dst = FILL ? out + offsets[q] : nullptr;
+        uint32_t *dst = FILL ? out + offsets[q] * (FILL == 2 ? 5u : 1u) : nullptr;
         if (lc != FLK_DROP && cy != FLK_DROP) {
             for_each_window_run(g, s.cell_start, lc, cy, k, [&](uint32_t rs, uint32_t re) {
                 for (uint32_t j = rs; j < re; ++j) {
@@ -1051,25 +1056,33 @@ __global__ void __launch_bounds__(128) k_query(const Geom g, const Store s, uint
                         const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
                         if (!(__fsqrt_rn(sq) <= dist)) continue;
                     }
-                    if (FILL) dst[n] = s.ids[j];
+                    if (FILL == 1) dst[n] = s.ids[j];
+                    if (FILL == 2) {
+                        const float4 o = reinterpret_cast<const float4 *>(s.rec)[j];
+                        uint32_t *d5 = dst + 5u * n;
+                        d5[0] = s.ids[j];
+                        d5[1] = __float_as_uint(o.x); d5[2] = __float_as_uint(o.y);
+                        d5[3] = __float_as_uint(o.z); d5[4] = __float_as_uint(o.w);
+                    }
                     ++n;
                 }
             });
         }
     }
-    if (!FILL) counts[q] = n;
+    if (FILL == 0) counts[q] = n;
 }
 
 void launch_query_count(const Geom &g, const Store &s, uint32_t nq, const float2 *loc, float dist, int relax,
                         uint32_t *counts, cudaStream_t st) {
     if (nq == 0) return;
-    k_query<false><<<(nq + 127) / 128, 128, 0, st>>>(g, s, nq, loc, dist, relax, counts, nullptr, nullptr);
+    k_query<0><<<(nq + 127) / 128, 128, 0, st>>>(g, s, nq, loc, dist, relax, counts, nullptr, nullptr);
 }
 
 void launch_query_fill(const Geom &g, const Store &s, uint32_t nq, const float2 *loc, float dist, int relax,
-                       const uint64_t *offsets, uint32_t *out, cudaStream_t st) {
+                       const uint64_t *offsets, uint32_t *out, cudaStream_t st, int objects) {
     if (nq == 0) return;
-    k_query<true><<<(nq + 127) / 128, 128, 0, st>>>(g, s, nq, loc, dist, relax, nullptr, offsets, out);
+    if (objects) k_query<2><<<(nq + 127) / 128, 128, 0, st>>>(g, s, nq, loc, dist, relax, nullptr, offsets, out);
+    else k_query<1><<<(nq + 127) / 128, 128, 0, st>>>(g, s, nq, loc, dist, relax, nullptr, offsets, out);
 }
 
 }  // namespace flk

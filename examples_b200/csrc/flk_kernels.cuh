@@ -58,7 +58,11 @@ constexpr uint32_t ERR_EXCHANGE = 2u;   // more border/migrating birds than `cap
 struct XHdr {
     uint32_t count, pad0, pad1, pad2;
 };
-__host__ __device__ inline size_t xbuf_bytes(uint32_t capx) { return sizeof(XHdr) + (size_t)capx * 20; }
+// message layout: XHdr | Rec[capx] | id[capx] | payload[capx * pw] (Field2D<O>: whatever else the object carries)
+__host__ __device__ inline size_t xbuf_bytes(uint32_t capx, uint32_t pw = 0) { return sizeof(XHdr) + (size_t)capx * (20 + 4 * (size_t)pw); }
+__host__ __device__ inline uint32_t *xbuf_pay(uint8_t *b, uint32_t capx) {
+    return reinterpret_cast<uint32_t *>(b + sizeof(XHdr) + (size_t)capx * 20);
+}
 __host__ __device__ inline Rec *xbuf_rec(uint8_t *b) { return reinterpret_cast<Rec *>(b + sizeof(XHdr)); }
 __host__ __device__ inline uint32_t *xbuf_id(uint8_t *b, uint32_t capx) {
     return reinterpret_cast<uint32_t *>(b + sizeof(XHdr) + (size_t)capx * 16);
@@ -88,7 +92,7 @@ void launch_gather_dense(const Store &s, uint32_t n_upper, uint32_t id0, uint32_
 void launch_unpack(const Geom &g, const Store &s, cudaStream_t st, int phase = 0);
 // tiles: the birds this rank owns are not an index range of the READ buffer: compact them (any of the outputs may be null)
 void launch_compact_owned(const Geom &g, const Store &s, uint32_t n_upper, uint32_t *out_id, float2 *out_loc, float2 *out_ld,
-                          uint32_t *counter, cudaStream_t st);
+                          uint32_t *counter, cudaStream_t st, uint32_t *out_pay = nullptr);
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st);
 // tiles: Bird::step for the two owned rows next to each row boundary of local columns [col_lo, col_hi) — the only
@@ -107,7 +111,8 @@ void launch_find(const Store &s, uint32_t n_upper, uint32_t id, float4 *out, uin
 void launch_split(const Store &s, uint32_t n, float2 *loc, float2 *ld, cudaStream_t st);
 void launch_query_count(const Geom &g, const Store &s, uint32_t nq, const float2 *loc, float dist, int relax,
                         uint32_t *counts, cudaStream_t st);
+// objects = 0: out[offsets[q] + k] = id; 1: out[5 * (offsets[q] + k) ..] = {id, loc.x, loc.y, last_d.x, last_d.y}
 void launch_query_fill(const Geom &g, const Store &s, uint32_t nq, const float2 *loc, float dist, int relax,
-                       const uint64_t *offsets, uint32_t *out, cudaStream_t st);
+                       const uint64_t *offsets, uint32_t *out, cudaStream_t st, int objects = 0);
 
 }  // namespace flk

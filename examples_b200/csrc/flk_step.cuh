@@ -42,11 +42,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 // append one bird to a neighbour's message (flockers_mpi/src/model/bird.rs:194: agents_to_send[owner].push)
-__device__ __forceinline__ void xbuf_append(const Store &s, uint8_t *buf, const Rec &r, uint32_t id) {
+__device__ __forceinline__ void xbuf_append(const Store &s, uint8_t *buf, const Rec &r, uint32_t id,
+                                            const uint32_t *payload = nullptr) {
     const uint32_t slot = atomicAdd(&reinterpret_cast<XHdr *>(buf)->count, 1u);
     if (slot < s.capx) {
         reinterpret_cast<float4 *>(xbuf_rec(buf))[slot] = make_float4(r.x, r.y, r.ldx, r.ldy);
         xbuf_id(buf, s.capx)[slot] = id;
+        for (uint32_t k = 0; k < s.pw; ++k) xbuf_pay(buf, s.capx)[(size_t)slot * s.pw + k] = payload ? payload[k] : 0u;
     } else {
         atomicOr(s.err_flag, ERR_EXCHANGE);
     }

@@ -161,20 +161,22 @@ class MgpuGroup:
     the strip logic is exercised on a single GPU)."""
 
     def __init__(self, width, height, discretization=DISCRETIZATION, capacity_per_rank=1 << 20, devices=(0, 0),
-                 col_bounds=None, tile_rows=1, row_bounds=None):
+                 col_bounds=None, tile_rows=1, row_bounds=None, payload_words=0):
         self._L = _lib.load()
         n = len(devices)
         self.n = n
+        self.payload_words = payload_words    # Field2D<O>: extra 32-bit words every object carries through the exchange
         self._arr = (C.c_void_p * n)()
         devs = (C.c_int * n)(*devices)
         cb = None if col_bounds is None else np.ascontiguousarray(col_bounds, dtype=np.int32)
         rb = None if row_bounds is None else np.ascontiguousarray(row_bounds, dtype=np.int32)
-        check(self._L.flk_mgpu_create_tiles(width, height, discretization, capacity_per_rank, n, devs, tile_rows, _vp(cb),
-                                            _vp(rb), self._arr))
+        check(self._L.flk_mgpu_create_ex(width, height, discretization, capacity_per_rank, n, devs, tile_rows, _vp(cb),
+                                         _vp(rb), 4 * payload_words, self._arr))
         self.fields = []
         for r in range(n):
             f = _StripField._adopt(C.c_void_p(self._arr[r]), width, height, discretization, capacity_per_rank)
             f.rank, f.world = r, n
+            f.payload_words = payload_words
             self.fields.append(f)
         self.mx, self.my, self.dh = self.fields[0].mx, self.fields[0].my, self.fields[0].dh
 
@@ -191,10 +193,27 @@ class MgpuGroup:
         for f in self.fields:
             f.set_math_mode(mode)
 
-    def set_objects(self, ids, loc, last_d):
+    def set_objects(self, ids, loc, last_d, payload=None):
         """init scatter (flockers_mpi state.rs:51-103): every strip is offered every bird and keeps the ones it owns"""
         for f in self.fields:
-            f.set_objects(ids, loc, last_d)
+            f.set_objects(ids, loc, last_d, payload)
+
+    def snapshot_by_id_with_payload(self):
+        """(ids, loc, last_d, payload[n, payload_words]) of the owned objects of every strip / tile, sorted by id"""
+        parts = []
+        for f in self.fields:
+            cap = f.capacity
+            ids = np.zeros(cap, dtype=np.uint32)
+            loc = np.zeros((cap, 2), dtype=np.float32)
+            ld = np.zeros((cap, 2), dtype=np.float32)
+            pay = np.zeros((cap, max(self.payload_words, 1)), dtype=np.uint32)
+            n = C.c_uint64()
+            check(self._L.flk_dist_snapshot_owned_ex(f._h, _vp(ids), _vp(loc), _vp(ld), _vp(pay), C.byref(n)))
+            k = n.value
+            parts.append((ids[:k], loc[:k], ld[:k], pay[:k, : self.payload_words]))
+        ids, loc, ld, pay = (np.concatenate([p[i] for p in parts]) for i in range(4))
+        o = np.argsort(ids, kind="stable")
+        return ids[o], loc[o], ld[o], pay[o]
 
     def scatter_objects(self, ids, loc, last_d):
         """init scatter done on the host like flockers_mpi's rank 0 (state.rs:65-92): every bird goes to the strip

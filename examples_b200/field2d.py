@@ -182,6 +182,42 @@ class Field2D:
     def get_neighbors_within_distance(self, loc: Real2D, dist: float) -> np.ndarray:
         return self._query(self._L.flk_get_neighbors_within_distance, loc, dist)
 
+    BIRD_DTYPE = np.dtype([("id", "<u4"), ("x", "<f4"), ("y", "<f4"), ("ldx", "<f4"), ("ldy", "<f4")])   # flk_bird
+
+    def get_neighbors_objects(self, loc: Real2D, dist: float, relax: bool = True) -> np.ndarray:
+        """what the reference's queries return: the objects themselves (`Vec<Bird>`, bird.rs:29-31), as a structured array
+        of flk_bird {id, x, y, ldx, ldy} in query order"""
+        fn = self._L.flk_get_neighbors_within_relax_distance_objects if relax else self._L.flk_get_neighbors_within_distance_objects
+        cap = 256
+        while True:
+            out = np.zeros(cap, dtype=self.BIRD_DTYPE)
+            n = C.c_uint32()
+            rc = fn(self._h, loc.x, loc.y, dist, _vp(out), cap, C.byref(n))
+            if rc == _lib.E_CAPACITY and n.value > cap:
+                cap = n.value
+                continue
+            check(rc)
+            return out[: n.value].copy()
+
+    def get_neighbors_birds(self, loc: Real2D, dist: float, relax: bool = True) -> list:
+        """the same as a list of Bird (the shape `for elem in vec` of bird.rs:52 consumes)"""
+        return [Bird(int(o["id"]), Real2D(float(o["x"]), float(o["y"])), Real2D(float(o["ldx"]), float(o["ldy"])))
+                for o in self.get_neighbors_objects(loc, dist, relax)]
+
+    def query_batch_objects(self, loc: np.ndarray, dist: float, relax: bool = True):
+        loc = np.ascontiguousarray(loc, dtype=np.float32)
+        nq = loc.size // 2
+        offsets = np.zeros(nq + 1, dtype=np.uint64)
+        cap = max(64 * nq, 1024)
+        while True:
+            out = np.zeros(cap, dtype=self.BIRD_DTYPE)
+            rc = self._L.flk_query_batch_objects(self._h, nq, _vp(loc), dist, int(relax), _vp(offsets), _vp(out), cap)
+            if rc == _lib.E_CAPACITY and int(offsets[nq]) > cap:
+                cap = int(offsets[nq])
+                continue
+            check(rc)
+            return offsets, out[: int(offsets[nq])]
+
     def query_batch(self, loc: np.ndarray, dist: float, relax: bool = True):
         loc = np.ascontiguousarray(loc, dtype=np.float32)
         nq = loc.size // 2

@@ -55,7 +55,8 @@ int flk_field_create(float width, float height, float discretization, int toroid
                      uint64_t capacity, int device, flk_field **out);
 /* Field2D<O> for an object type that carries more than Bird's {id, loc, last_d} (template/src/model/crab.rs:11-19,
  * virusnetwork/src/model/node.rs): payload_bytes (multiple of 4, <= 256) opaque bytes per object travel with it through
- * set_object_location, Bird::step (copied unchanged to the successor) and lazy_update.  Single-GPU handles only. */
+ * set_object_location, Bird::step (copied unchanged to the successor) and lazy_update; on strips and tiles
+ * (flk_dist_create_ex / flk_mgpu_create_ex) they also travel in the halo and migration messages. */
 int flk_field_create_ex(float width, float height, float discretization, int toroidal, uint64_t capacity, int device,
                         uint32_t payload_bytes, flk_field **out);
 int flk_field_destroy(flk_field *f);
@@ -140,9 +141,24 @@ int flk_get_neighbors_within_relax_distance(flk_field *f, float x, float y, floa
 int flk_get_neighbors_within_distance(flk_field *f, float x, float y, float dist,
                                       uint32_t *ids, uint32_t cap, uint32_t *n);
 
-/* batched query for nq HOST locations (interleaved x,y): offsets[nq+1], ids[cap] (CSR) */
+/* The same queries returning what the reference returns: the objects themselves (bird.rs:29-31 iterates `Vec<Bird>` and
+ * reads elem.loc and elem.last_d, bird.rs:52-71).  flk_bird is Bird {id, loc, last_d} (bird.rs:13-18) in its 20-byte wire
+ * form (flockers_mpi/src/model/bird.rs:31-57), as stored in the READ buffer; same order and error behaviour as above. */
+typedef struct flk_bird {
+    uint32_t id;
+    float x, y;             /* loc */
+    float last_dx, last_dy; /* last_d */
+} flk_bird;
+int flk_get_neighbors_within_relax_distance_objects(flk_field *f, float x, float y, float dist,
+                                                    flk_bird *objects, uint32_t cap, uint32_t *n);
+int flk_get_neighbors_within_distance_objects(flk_field *f, float x, float y, float dist,
+                                              flk_bird *objects, uint32_t cap, uint32_t *n);
+
+/* batched query for nq HOST locations (interleaved x,y): offsets[nq+1], ids[cap] (CSR); _objects: flk_bird objects[cap] */
 int flk_query_batch(flk_field *f, uint64_t nq, const float *loc, float dist, int relax,
                     uint64_t *offsets, uint32_t *ids, uint64_t cap);
+int flk_query_batch_objects(flk_field *f, uint64_t nq, const float *loc, float dist, int relax,
+                            uint64_t *offsets, flk_bird *objects, uint64_t cap);
 
 /* number of objects in the READ buffer */
 int flk_num_objects(const flk_field *f, uint64_t *n);
@@ -238,6 +254,10 @@ int flk_dist_create_cols(float width, float height, float discretization, uint64
 int flk_dist_create_tiles(float width, float height, float discretization, uint64_t capacity, int device,
                           int rank, int world, const uint8_t id128[128], int tile_rows, const int32_t *col_bounds,
                           const int32_t *row_bounds, flk_field **out);
+/* flk_dist_create_tiles with payload_bytes opaque bytes per object (see flk_field_create_ex); tile_rows = 1: strips */
+int flk_dist_create_ex(float width, float height, float discretization, uint64_t capacity, int device,
+                       int rank, int world, const uint8_t id128[128], int tile_rows, const int32_t *col_bounds,
+                       const int32_t *row_bounds, uint32_t payload_bytes, flk_field **out);
 /* global cell range [col0,col1) x [row0,row1) owned by this rank (strips: all rows) */
 int flk_dist_tile(const flk_field *f, int32_t *col0, int32_t *col1, int32_t *row0, int32_t *row1);
 
@@ -267,6 +287,9 @@ int flk_dist_num_owned(flk_field *f, uint64_t *n);
  * out of the READ buffer in no particular order (sort by id if an order is needed). */
 int flk_dist_snapshot_owned(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n);
 
+/* flk_dist_snapshot_owned plus the payload bytes of the owned objects, same order */
+int flk_dist_snapshot_owned_ex(flk_field *f, uint32_t *id, float *loc, float *last_d, void *payload, uint64_t *n);
+
 /* as above, but the copies of the records are only enqueued: *n is exact on return (the call waits for the tick that
  * produced the READ buffer), the HOST arrays (pinned) are valid after flk_synchronize */
 int flk_dist_snapshot_owned_async(flk_field *f, uint32_t *id, float *loc, float *last_d, uint64_t *n);
@@ -280,6 +303,9 @@ int flk_mgpu_create_cols(float width, float height, float discretization, uint64
 int flk_mgpu_create_tiles(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
                           const int *devices, int tile_rows, const int32_t *col_bounds, const int32_t *row_bounds,
                           flk_field **out);
+int flk_mgpu_create_ex(float width, float height, float discretization, uint64_t capacity_per_rank, int n,
+                       const int *devices, int tile_rows, const int32_t *col_bounds, const int32_t *row_bounds,
+                       uint32_t payload_bytes, flk_field **out);
 int flk_mgpu_commit(flk_field **handles, int n);
 int flk_mgpu_step(flk_field **handles, int n, uint64_t step, uint64_t seed, const float *injected_r,
                   uint64_t n_injected);

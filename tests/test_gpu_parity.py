@@ -367,3 +367,38 @@ def test_full_size_properties(n, W, ticks):
     sp = np.hypot(g["ldx"].astype(np.float64), g["ldy"].astype(np.float64))
     assert np.all(np.abs(sp - 0.7) < 1e-6)
     assert g["x"].min() >= 0 and g["x"].max() <= W and g["y"].min() >= 0 and g["y"].max() <= W
+
+
+@pytest.mark.parametrize("relax", [True, False])
+def test_queries_return_the_objects_themselves(relax):
+    """bird.rs:29-31,52-71: the reference's queries return Vec<Bird> and Bird::step reads elem.loc / elem.last_d.
+    flk_get_neighbors_within_*_objects returns the same objects in the same order, bit for bit"""
+    import ctypes as C
+    from examples_b200 import Real2D, _lib
+    W = 200.0
+    birds = clustered_birds(3000, W, W)                   # non-zero headings
+    f = load_gpu(birds, W, W)
+    fo = oracle_field(birds, W, W)
+    rng = np.random.default_rng(12)
+    probes = np.concatenate([np.stack([birds["x"], birds["y"]], 1)[:150], (rng.random((50, 2)) * W).astype(np.float32),
+                             np.array([[0.0, 0.0], [W, W], [0.01, W - 0.01]], dtype=np.float32)])
+    off, objs = f.query_batch_objects(probes, 10.0, relax=relax)
+    assert objs.dtype.itemsize == 20
+    for q, (x, y) in enumerate(probes):
+        want = fo.neighbors(x, y, 10.0, relax=relax)
+        got = objs[int(off[q]):int(off[q + 1])]
+        assert got.tobytes() == np.ascontiguousarray(want).tobytes(), (q, x, y)
+        if q % 40 == 0:
+            one = f.get_neighbors_objects(Real2D(float(x), float(y)), 10.0, relax=relax)
+            assert one.tobytes() == got.tobytes()
+    b = f.get_neighbors_birds(Real2D(100.0, 100.0), 10.0, relax=relax)
+    want = fo.neighbors(100.0, 100.0, 10.0, relax=relax)
+    assert [o.id for o in b] == list(want["id"]) and all(o.last_d.x == w["ldx"] for o, w in zip(b, want))
+    # capacity behaviour: full size reported, the first `cap` objects valid
+    out = np.zeros(3, dtype=f.BIRD_DTYPE)
+    n = C.c_uint32()
+    fn = f._L.flk_get_neighbors_within_relax_distance_objects if relax else f._L.flk_get_neighbors_within_distance_objects
+    rc = fn(f._h, 100.0, 100.0, 10.0, C.c_void_p(out.ctypes.data), 3, C.byref(n))
+    assert n.value == len(want)
+    if len(want) > 3:
+        assert rc == _lib.E_CAPACITY and out.tobytes() == np.ascontiguousarray(want[:3]).tobytes()

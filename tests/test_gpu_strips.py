@@ -281,3 +281,36 @@ def test_tiles_clustered_with_uneven_boundaries():
         g.run(t0, 10)
         assert bits_equal(from_arrays(*g.snapshot_by_id()), from_arrays(*f.snapshot_by_id())), t0
     g.close()
+
+
+@pytest.mark.parametrize("tile_rows", [1, 2])
+def test_payload_travels_through_the_halo_and_migration_messages(tile_rows):
+    """Field2D<O> with an object larger than Bird (template/src/model/crab.rs:11-19): its extra bytes follow it through
+    Bird::step, through the strip / tile exchange (migrants AND ghosts, two hops on tiles) and through lazy_update"""
+    from examples_b200 import Field2D
+    from examples_b200.distributed import MgpuGroup
+    from tests.helpers import clustered_birds
+    W = 100.0
+    n = 3000
+    birds = clustered_birds(n, W, W, seed=21, per_cluster=150, sigma=6.0)        # headings: heavy migration
+    ids, loc, ld = to_arrays(birds)
+    pay = np.stack([ids * np.uint32(2654435761) + np.uint32(17), ~ids, ids ^ np.uint32(0xA5A5A5A5)], axis=1).astype(np.uint32)
+    single = Field2D(W, W, D, True, capacity=n, payload_words=3)
+    single.set_objects(ids, loc, ld, pay)
+    single.lazy_update()
+    g = MgpuGroup(W, W, D, capacity_per_rank=n, devices=[0, 0, 0, 0], tile_rows=tile_rows, payload_words=3)
+    g.set_objects(ids, loc, ld, pay)
+    g.commit()
+    for t in range(25):
+        single.step(t)
+        single.lazy_update()
+        g.step(t)
+    s_id, s_loc, s_ld, s_pay = single.snapshot_with_payload()
+    o = np.argsort(s_id, kind="stable")
+    g_id, g_loc, g_ld, g_pay = g.snapshot_by_id_with_payload()
+    assert np.array_equal(g_id, ids) and np.array_equal(s_id[o], ids)
+    assert np.array_equal(g_pay, pay), "a payload was lost or attached to the wrong object on the way"
+    assert np.array_equal(s_pay[o], pay)
+    assert bits_equal(from_arrays(g_id, g_loc, g_ld), from_arrays(s_id[o], s_loc[o], s_ld[o]))
+    moved = np.abs(g_loc - loc).max()
+    assert moved > 5.0                                                            # birds did cross strip boundaries
