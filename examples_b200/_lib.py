@@ -27,6 +27,7 @@ SIGNATURES = {
     "flk_field_clear": [_vp],
     "flk_set_params": [_vp, _f32, _f32, _f32, _f32, _f32, _f32, _f32, C.c_int],
     "flk_set_math_mode": [_vp, C.c_int],
+    "flk_set_engine_semantics": [_vp, C.c_int],
     "flk_field_dims": [_vp, _P(_i32), _P(_i32), _P(_i32), _P(_i32)],
     "flk_set_layout": [_vp, C.c_int],
     "flk_get_layout": [_vp, _P(_i32), _P(_i32), _P(_u32)],

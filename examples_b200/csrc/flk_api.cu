@@ -294,6 +294,7 @@ int update_window(flk_field *f) {
     const float q = std::floor(f->p.radius / f->g.d);
     int k = (q != q) ? 0 : (int)q;
     if (k < 0) k = 0;
+    k += f->g.wplus1;                                   // [EXT] E3 alternative (flk_set_engine_semantics)
     if (f->p.radius > 0.0f && (2 * k + 1 > f->g.mx || 2 * k + 1 > f->g.my) && f->g.toroidal)
         return fail(FLK_E_UNSUPPORTED, "query window (%d cells) wider than the grid (%d x %d): duplicate visits are not implemented",
                     2 * k + 1, f->g.mx, f->g.my);
@@ -583,6 +584,19 @@ int flk_set_params(flk_field *f, float cohesion, float avoidance, float randomne
         rc = demote_to_runs(f);
         if (rc) { f->p = old; return rc; }
     }
+    return FLK_OK;
+}
+
+int flk_set_engine_semantics(flk_field *f, int window_plus1) {
+    CHECK_HANDLE(f);
+    if (window_plus1 != 0 && window_plus1 != 1) return fail(FLK_E_INVALID, "window_plus1 must be 0 or 1");
+    const int old = f->g.wplus1;
+    f->g.wplus1 = window_plus1;
+    int rc = update_window(f);
+    if (rc) { f->g.wplus1 = old; update_window(f); return rc; }
+    f->graph_valid = false;
+    f->sgraph_valid[0] = f->sgraph_valid[1] = false;
+    if (f->layout == 1 && !slots_params_ok(f)) return demote_to_runs(f);
     return FLK_OK;
 }
 
@@ -912,7 +926,7 @@ static int query_batch_impl(flk_field *f, uint64_t nq, const float *loc, float d
     if (nq == 0) return FLK_OK;
     if (int rc0 = ensure_view(f)) return rc0;
     if (dist > 0.0f) {
-        const int k = (int)std::floor(dist / f->g.d);
+        const int k = (int)std::floor(dist / f->g.d) + f->g.wplus1;
         if (f->g.toroidal && (2 * k + 1 > f->g.mx || 2 * k + 1 > f->g.my))
             return fail(FLK_E_UNSUPPORTED, "query window wider than the grid");
         if (f->g.mode != 0 && k > 1) return fail(FLK_E_UNSUPPORTED, "dist handles answer queries with k<=1 only");

@@ -1034,7 +1034,7 @@ __global__ void __launch_bounds__(128) k_query(const Geom g, const Store s, uint
     const float2 l = loc[q];
     uint32_t n = 0;
     if (dist > 0.0f) {
-        const int k = __float2int_rz(floorf(__fdiv_rn(dist, g.d)));
+        const int k = __float2int_rz(floorf(__fdiv_rn(dist, g.d))) + g.wplus1;
         const int gcx = cell_coord(l.x, g.d, g.mx + 1);
         const int cy = local_row(g, cell_coord(l.y, g.d, g.dhg));   // row of the local cell arrays
         const int lc = local_col(g, gcx);

@@ -97,6 +97,10 @@ class Field2D:
                    momentum=MOMENTUM, jump=JUMP, radius=10.0, relax=True):
         check(self._L.flk_set_params(self._h, cohesion, avoidance, randomness, consistency, momentum, jump, radius, int(relax)))
 
+    def set_engine_semantics(self, window_plus1: bool = False):
+        """[EXT] E3 of SURVEY.md §8c: query window of floor(dist/d) (+1 if window_plus1) cells on either side"""
+        check(self._L.flk_set_engine_semantics(self._h, int(window_plus1)))
+
     def set_math_mode(self, mode: int):
         check(self._L.flk_set_math_mode(self._h, mode))
 

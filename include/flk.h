@@ -70,6 +70,12 @@ int flk_field_clear(flk_field *f);
 int flk_set_params(flk_field *f, float cohesion, float avoidance, float randomness, float consistency,
                    float momentum, float jump, float radius, int relax);
 
+/* Engine semantics that could not be read off the reference (the krabmaga crate is not vendored; SURVEY.md §8c lists them
+ * as E1..E11).  window_plus1 (E3): 0 (default) = the query window spans floor(dist / discretization) cells on either side,
+ * 1 = one more (MASON's Continuous2D).  The parity-pinning kit finds out which one the real engine uses;
+ * the CPU restatement under oracle/ carries the same switch plus the ones for E4 / E5. */
+int flk_set_engine_semantics(flk_field *f, int window_plus1);
+
 /* 0 = exact (default): every f32 operation of Bird::step is one IEEE-754 round-to-nearest operation, no FMA
  *     contraction, evaluated in the reference's order with the neighbours of a cell visited in ascending id (the
  *     canonical bag order).  Results are bit-identical to the repository's CPU oracle (oracle/), which

@@ -48,12 +48,15 @@ typedef struct {
     int relax;          /* 1 = get_neighbors_within_relax_distance (shipped), 0 = exact query */
     int window_plus1;   /* E3: 0 = floor(dist/d) (krabmaga), 1 = floor(dist/d)+1 (MASON) */
     int canonical_bags; /* 1 = keep bags sorted by id */
+    int wrap_with_slack;/* E4: 0 = window indices wrap modulo ceil(W/d) (recalled), 1 = modulo ceil(W/d)+1 (slack cell on the ring) */
+    int slack_to_zero;  /* E5: 0 = a location with cell index ceil(W/d) stays in the slack cell (recalled), 1 = it wraps to cell 0 */
 } orc_cfg;
 
 ORC_API void orc_cfg_default(orc_cfg *c) {
     c->cohesion = 0.8f; c->avoidance = 1.0f; c->randomness = 1.1f;
     c->consistency = 0.7f; c->momentum = 1.0f; c->jump = 0.7f;
     c->radius = 10.0f; c->relax = 1; c->window_plus1 = 0; c->canonical_bags = 1;
+    c->wrap_with_slack = 0; c->slack_to_zero = 0;
 }
 
 /* Rust `f as i32`: saturating, NaN -> 0 */
@@ -130,6 +133,7 @@ typedef struct {
     orc_bag *bags[2];
     int read, write;
     int canonical;
+    int e4_wrap_with_slack, e5_slack_to_zero; /* [EXT] alternatives, see orc_cfg (defaults 0 = recalled upstream behaviour) */
 } orc_field;
 
 ORC_API orc_field *orc_field_new(float w, float h, float d, int toroidal, int canonical) {
@@ -161,10 +165,20 @@ ORC_API void orc_field_dims(const orc_field *f, int *dw, int *dh, int *mx, int *
     *dw = f->dw; *dh = f->dh; *mx = f->mx; *my = f->my;
 }
 
-/* E1: cell of a location */
+/* E1: cell of a location (E5 alternative: the slack index wraps to 0) */
 static inline void discretize(const orc_field *f, float x, float y, int *cx, int *cy) {
     *cx = f2i_sat(floorf(x / f->disc));
     *cy = f2i_sat(floorf(y / f->disc));
+    if (f->e5_slack_to_zero) {
+        if (*cx == f->mx) *cx = 0;
+        if (*cy == f->my) *cy = 0;
+    }
+}
+
+/* the [EXT] alternatives of E4 / E5 (parity-pinning kit: which setting reproduces a dump of the real engine?) */
+ORC_API void orc_field_set_semantics(orc_field *f, int wrap_with_slack, int slack_to_zero) {
+    f->e4_wrap_with_slack = wrap_with_slack;
+    f->e5_slack_to_zero = slack_to_zero;
 }
 
 ORC_API void orc_discretize(const orc_field *f, float x, float y, int *cx, int *cy) { discretize(f, x, y, cx, cy); }
@@ -260,7 +274,10 @@ static void query(const orc_field *f, float x, float y, float dist, int relax, i
     for (int i = cx - k; i <= cx + k; ++i) {
         for (int j = cy - k; j <= cy + k; ++j) {
             int bx = i, by = j;
-            if (f->toroidal) { bx = wrap_mod(i, f->mx); by = wrap_mod(j, f->my); }
+            if (f->toroidal) {
+                bx = wrap_mod(i, f->e4_wrap_with_slack ? f->dw : f->mx);
+                by = wrap_mod(j, f->e4_wrap_with_slack ? f->dh : f->my);
+            }
             else if (i < 0 || j < 0 || i >= f->dw || j >= f->dh) continue;
             const orc_bag *b = &f->bags[f->read][(size_t)bx * (size_t)f->dh + (size_t)by];
             for (uint32_t e = 0; e < b->n; ++e) {
@@ -382,6 +399,7 @@ ORC_API orc_sim *orc_sim_new(float w, float h, float d, int toroidal, const orc_
     orc_sim *s = (orc_sim *)calloc(1, sizeof(orc_sim));
     s->cfg = *cfg;
     s->field = orc_field_new(w, h, d, toroidal, cfg->canonical_bags);
+    orc_field_set_semantics(s->field, cfg->wrap_with_slack, cfg->slack_to_zero);
     return s;
 }
 

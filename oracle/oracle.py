@@ -24,6 +24,7 @@ class Cfg(C.Structure):
         ("cohesion", C.c_float), ("avoidance", C.c_float), ("randomness", C.c_float),
         ("consistency", C.c_float), ("momentum", C.c_float), ("jump", C.c_float),
         ("radius", C.c_float), ("relax", C.c_int), ("window_plus1", C.c_int), ("canonical_bags", C.c_int),
+        ("wrap_with_slack", C.c_int), ("slack_to_zero", C.c_int),
     ]
 
 
@@ -52,6 +53,7 @@ def lib() -> C.CDLL:
             "orc_draw": (None, [u64, u32, u64, C.POINTER(f32), C.POINTER(f32)]),
             "orc_field_new": (vp, [f32, f32, f32, i32, i32]),
             "orc_field_free": (None, [vp]),
+            "orc_field_set_semantics": (None, [vp, i32, i32]),
             "orc_field_dims": (None, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
             "orc_discretize": (None, [vp, f32, f32, C.POINTER(i32), C.POINTER(i32)]),
             "orc_set_object_location": (None, [vp, vp, f32, f32]),
@@ -142,6 +144,10 @@ class Field:
         if getattr(self, "_own", False) and self.h:
             lib().orc_field_free(self.h)
             self.h = None
+
+    def set_semantics(self, wrap_with_slack=False, slack_to_zero=False):
+        """the [EXT] alternatives E4 / E5 of SURVEY.md §8c (defaults = recalled upstream behaviour)"""
+        lib().orc_field_set_semantics(self.h, int(wrap_with_slack), int(slack_to_zero))
 
     def discretize(self, x, y):
         cx, cy = C.c_int(), C.c_int()

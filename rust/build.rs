@@ -15,7 +15,7 @@ fn main() {
             "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-o",
         ])
         .arg(&lib)
-        .args(["flk_kernels.cu", "flk_api.cu", "flk_dist.cu"])
+        .args(["flk_kernels.cu", "flk_slots.cu", "flk_api.cu", "flk_dist.cu"])
         .status()
         .expect("nvcc not found: libflk has no CPU fallback");
     assert!(status.success(), "nvcc failed");
@@ -23,7 +23,8 @@ fn main() {
     println!("cargo:rustc-link-lib=dylib=flk");
     // the library stays in OUT_DIR: give binaries and examples of this crate an rpath to it
     println!("cargo:rustc-link-arg=-Wl,-rpath,{}", out.display());
-    for f in ["flk_kernels.cu", "flk_api.cu", "flk_dist.cu", "flk_device.cuh", "flk_kernels.cuh", "flk_internal.cuh"] {
+    for f in ["flk_kernels.cu", "flk_slots.cu", "flk_api.cu", "flk_dist.cu", "flk_device.cuh", "flk_kernels.cuh", "flk_step.cuh",
+              "flk_slots.cuh", "flk_internal.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include").join("flk.h").display());

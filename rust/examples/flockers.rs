@@ -2,17 +2,29 @@
 //!   - `field1: Field2D<Bird>`            ->  `field1: GpuField2D<Bird>`
 //!   - N x `schedule_repeating(bird)`     ->  1 x `schedule_repeating(FlockStepper)`
 //! `main`, `Flocker::new`, `init`, `update`, `simulate_old!` are unchanged.
-use krabmaga::engine::{location::Real2D, schedule::Schedule, state::State};
+use krabmaga::engine::{location::{Location2D, Real2D}, schedule::Schedule, state::State};
 use krabmaga::rand::{self, Rng};
 use krabmaga::*;
 use krabmaga_flk::{FlockObject, FlockStepper, GpuField2D, HasGpuField};
 use std::any::Any;
+use std::fmt;
+use std::hash::{Hash, Hasher};
 
 pub static DISCRETIZATION: f32 = 10.0 / 1.5;
 pub static TOROIDAL: bool = true;
 
 #[derive(Clone, Copy)]
 pub struct Bird { pub id: u32, pub loc: Real2D, pub last_d: Real2D }
+
+// bird.rs:148-176, unchanged: identity, hash and equality by id; Location2D
+impl Hash for Bird { fn hash<H: Hasher>(&self, state: &mut H) { self.id.hash(state); } }
+impl PartialEq for Bird { fn eq(&self, other: &Bird) -> bool { self.id == other.id } }
+impl Eq for Bird {}
+impl Location2D<Real2D> for Bird {
+    fn get_location(self) -> Real2D { self.loc }
+    fn set_location(&mut self, loc: Real2D) { self.loc = loc; }
+}
+impl fmt::Display for Bird { fn fmt(&self, f: &mut fmt::Formatter) -> fmt::Result { write!(f, "{}", self.id) } }
 
 impl FlockObject for Bird {
     fn id(&self) -> u32 { self.id }

@@ -7,6 +7,17 @@ pub struct flk_field {
     _private: [u8; 0],
 }
 
+/// Bird {id, loc, last_d} (flockers/src/model/bird.rs:13-18) in its 20-byte wire form (flockers_mpi/src/model/bird.rs:31-57)
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
+pub struct flk_bird {
+    pub id: u32,
+    pub x: c_float,
+    pub y: c_float,
+    pub last_dx: c_float,
+    pub last_dy: c_float,
+}
+
 pub const FLK_OK: c_int = 0;
 pub const FLK_E_CAPACITY: c_int = -3;
 
@@ -19,7 +30,10 @@ extern "C" {
     pub fn flk_field_clear(f: *mut flk_field) -> c_int;
     pub fn flk_set_params(f: *mut flk_field, cohesion: c_float, avoidance: c_float, randomness: c_float,
                           consistency: c_float, momentum: c_float, jump: c_float, radius: c_float, relax: c_int) -> c_int;
+    pub fn flk_set_engine_semantics(f: *mut flk_field, window_plus1: c_int) -> c_int;
     pub fn flk_set_math_mode(f: *mut flk_field, mode: c_int) -> c_int;
+    pub fn flk_set_layout(f: *mut flk_field, layout: c_int) -> c_int;
+    pub fn flk_get_layout(f: *mut flk_field, layout: *mut i32, slots_per_cell: *mut i32, totals: *mut u32) -> c_int;
     pub fn flk_field_dims(f: *const flk_field, dw: *mut i32, dh: *mut i32, mx: *mut i32, my: *mut i32) -> c_int;
     pub fn flk_set_object_location(f: *mut flk_field, id: u32, x: c_float, y: c_float, ldx: c_float, ldy: c_float) -> c_int;
     pub fn flk_set_objects(f: *mut flk_field, n: u64, id: *const u32, loc: *const c_float, last_d: *const c_float) -> c_int;
@@ -34,8 +48,14 @@ extern "C" {
                                                    ids: *mut u32, cap: u32, n: *mut u32) -> c_int;
     pub fn flk_get_neighbors_within_distance(f: *mut flk_field, x: c_float, y: c_float, dist: c_float,
                                              ids: *mut u32, cap: u32, n: *mut u32) -> c_int;
+    pub fn flk_get_neighbors_within_relax_distance_objects(f: *mut flk_field, x: c_float, y: c_float, dist: c_float,
+                                                           objects: *mut flk_bird, cap: u32, n: *mut u32) -> c_int;
+    pub fn flk_get_neighbors_within_distance_objects(f: *mut flk_field, x: c_float, y: c_float, dist: c_float,
+                                                     objects: *mut flk_bird, cap: u32, n: *mut u32) -> c_int;
     pub fn flk_query_batch(f: *mut flk_field, nq: u64, loc: *const c_float, dist: c_float, relax: c_int,
                            offsets: *mut u64, ids: *mut u32, cap: u64) -> c_int;
+    pub fn flk_query_batch_objects(f: *mut flk_field, nq: u64, loc: *const c_float, dist: c_float, relax: c_int,
+                                   offsets: *mut u64, objects: *mut flk_bird, cap: u64) -> c_int;
     pub fn flk_num_objects(f: *const flk_field, n: *mut u64) -> c_int;
     pub fn flk_snapshot(f: *mut flk_field, id: *mut u32, loc: *mut c_float, last_d: *mut c_float, n: *mut u64) -> c_int;
     pub fn flk_snapshot_async(f: *mut flk_field, id: *mut u32, loc: *mut c_float, last_d: *mut c_float, n: *mut u64) -> c_int;
@@ -67,6 +87,9 @@ extern "C" {
     pub fn flk_dist_create_tiles(width: c_float, height: c_float, discretization: c_float, capacity: u64, device: c_int,
                                  rank: c_int, world: c_int, id128: *const u8, tile_rows: c_int, col_bounds: *const i32,
                                  row_bounds: *const i32, out: *mut *mut flk_field) -> c_int;
+    pub fn flk_dist_create_ex(width: c_float, height: c_float, discretization: c_float, capacity: u64, device: c_int,
+                              rank: c_int, world: c_int, id128: *const u8, tile_rows: c_int, col_bounds: *const i32,
+                              row_bounds: *const i32, payload_bytes: u32, out: *mut *mut flk_field) -> c_int;
     pub fn flk_dist_tile(f: *const flk_field, col0: *mut i32, col1: *mut i32, row0: *mut i32, row1: *mut i32) -> c_int;
     pub fn flk_mgpu_create_tiles(width: c_float, height: c_float, discretization: c_float, capacity_per_rank: u64, n: c_int,
                                  devices: *const c_int, tile_rows: c_int, col_bounds: *const i32, row_bounds: *const i32,
@@ -82,8 +105,13 @@ extern "C" {
     pub fn flk_dist_num_owned(f: *mut flk_field, n: *mut u64) -> c_int;
     pub fn flk_dist_snapshot_owned(f: *mut flk_field, id: *mut u32, loc: *mut c_float, last_d: *mut c_float, n: *mut u64) -> c_int;
     pub fn flk_dist_snapshot_owned_async(f: *mut flk_field, id: *mut u32, loc: *mut c_float, last_d: *mut c_float, n: *mut u64) -> c_int;
+    pub fn flk_dist_snapshot_owned_ex(f: *mut flk_field, id: *mut u32, loc: *mut c_float, last_d: *mut c_float,
+                                      payload: *mut c_void, n: *mut u64) -> c_int;
     pub fn flk_mgpu_create(width: c_float, height: c_float, discretization: c_float, capacity_per_rank: u64, n: c_int,
                            devices: *const c_int, out: *mut *mut flk_field) -> c_int;
+    pub fn flk_mgpu_create_ex(width: c_float, height: c_float, discretization: c_float, capacity_per_rank: u64, n: c_int,
+                              devices: *const c_int, tile_rows: c_int, col_bounds: *const i32, row_bounds: *const i32,
+                              payload_bytes: u32, out: *mut *mut flk_field) -> c_int;
     pub fn flk_mgpu_commit(handles: *mut *mut flk_field, n: c_int) -> c_int;
     pub fn flk_mgpu_step(handles: *mut *mut flk_field, n: c_int, step: u64, seed: u64, injected_r: *const c_float,
                          n_injected: u64) -> c_int;

@@ -11,14 +11,19 @@ pub mod ffi;
 pub mod dist;
 
 use krabmaga::engine::agent::Agent;
-use krabmaga::engine::location::Real2D;
+use krabmaga::engine::location::{Location2D, Real2D};
 use krabmaga::engine::state::State;
 use std::cell::Cell;
 use std::ffi::CStr;
+use std::fmt::Display;
+use std::hash::Hash;
 use std::ptr;
 
-/// What the field stores per object: krABMaga's `Bird { id, loc, last_d }` (bird.rs:13-18).
-pub trait FlockObject: Copy {
+/// What the field stores per object.  The bounds are the reference's own for `Field2D<O>`
+/// (`O: Location2D<Real2D> + Clone + Copy + Hash + Eq + Display`, as `impl`ed for Bird at bird.rs:148-176); the three
+/// methods are what the device needs beyond them: the u32 the object is hashed and compared by (bird.rs:148-163), its
+/// heading, and a way to rebuild the object from the record the device keeps (Bird is exactly {id, loc, last_d}).
+pub trait FlockObject: Location2D<Real2D> + Copy + Hash + Eq + Display {
     fn id(&self) -> u32;
     fn last_d(&self) -> Real2D;
     fn from_parts(id: u32, loc: Real2D, last_d: Real2D) -> Self;
@@ -38,6 +43,10 @@ pub struct GpuField2D<O: FlockObject> {
     _o: std::marker::PhantomData<O>,
 }
 
+fn object_of<O: FlockObject>(b: &ffi::flk_bird) -> O {
+    O::from_parts(b.id, Real2D { x: b.x, y: b.y }, Real2D { x: b.last_dx, y: b.last_dy })
+}
+
 impl<O: FlockObject> GpuField2D<O> {
     /// `Field2D::new(w, h, discretization, toroidal)` + the capacity the device store is sized for.
     pub fn new(width: f32, height: f32, discretization: f32, toroidal: bool, capacity: u64) -> Self {
@@ -50,21 +59,40 @@ impl<O: FlockObject> GpuField2D<O> {
         let d = object.last_d();
         check(unsafe { ffi::flk_set_object_location(self.h, object.id(), loc.x, loc.y, d.x, d.y) });
     }
-    pub fn get_neighbors_within_relax_distance(&self, loc: Real2D, dist: f32) -> Vec<u32> { self.query(loc, dist, true) }
-    pub fn get_neighbors_within_distance(&self, loc: Real2D, dist: f32) -> Vec<u32> { self.query(loc, dist, false) }
-    fn query(&self, loc: Real2D, dist: f32, relax: bool) -> Vec<u32> {
-        let mut ids = vec![0u32; 256];
+    /// `Field2D::get_neighbors_within_relax_distance(loc, dist) -> Vec<O>` (bird.rs:29-31): the objects themselves, in
+    /// query order, as the READ buffer holds them (Bird::step reads `elem.loc` and `elem.last_d`, bird.rs:52-71).
+    pub fn get_neighbors_within_relax_distance(&self, loc: Real2D, dist: f32) -> Vec<O> { self.query(loc, dist, true) }
+    /// `Field2D::get_neighbors_within_distance(loc, dist) -> Vec<O>`
+    pub fn get_neighbors_within_distance(&self, loc: Real2D, dist: f32) -> Vec<O> { self.query(loc, dist, false) }
+    fn query(&self, loc: Real2D, dist: f32, relax: bool) -> Vec<O> {
+        let mut buf = vec![ffi::flk_bird::default(); 256];
         loop {
             let mut n = 0u32;
             let rc = unsafe {
-                if relax { ffi::flk_get_neighbors_within_relax_distance(self.h, loc.x, loc.y, dist, ids.as_mut_ptr(), ids.len() as u32, &mut n) }
-                else { ffi::flk_get_neighbors_within_distance(self.h, loc.x, loc.y, dist, ids.as_mut_ptr(), ids.len() as u32, &mut n) }
+                if relax { ffi::flk_get_neighbors_within_relax_distance_objects(self.h, loc.x, loc.y, dist, buf.as_mut_ptr(), buf.len() as u32, &mut n) }
+                else { ffi::flk_get_neighbors_within_distance_objects(self.h, loc.x, loc.y, dist, buf.as_mut_ptr(), buf.len() as u32, &mut n) }
             };
-            if rc == ffi::FLK_E_CAPACITY && n as usize > ids.len() { ids.resize(n as usize, 0); continue; }
+            if rc == ffi::FLK_E_CAPACITY && n as usize > buf.len() { buf.resize(n as usize, ffi::flk_bird::default()); continue; }
             check(rc);
-            ids.truncate(n as usize);
-            return ids;
+            return buf[..n as usize].iter().map(object_of::<O>).collect();
         }
+    }
+    /// `Field2D::get(&object) -> Option<&O>` (visualization/vis_state.rs:52); by value here: the stored copy lives on the device
+    pub fn get(&self, object: &O) -> Option<O> {
+        let (mut out, mut found) = ([0f32; 4], 0i32);
+        check(unsafe { ffi::flk_get_object(self.h, object.id(), out.as_mut_ptr(), &mut found) });
+        if found == 0 { return None; }
+        Some(O::from_parts(object.id(), Real2D { x: out[0], y: out[1] }, Real2D { x: out[2], y: out[3] }))
+    }
+    /// `Field2D::get_location(object) -> Option<Real2D>` (visualization/bird_vis.rs:23)
+    pub fn get_location(&self, object: O) -> Option<Real2D> {
+        self.get(&object).map(|o| o.get_location())
+    }
+    /// `Field2D::num_objects()`
+    pub fn num_objects(&self) -> usize {
+        let mut n = 0u64;
+        check(unsafe { ffi::flk_num_objects(self.h, &mut n) });
+        n as usize
     }
     /// `Field::lazy_update` (state.rs:54-56)
     pub fn lazy_update(&mut self) { check(unsafe { ffi::flk_lazy_update(self.h) }); }

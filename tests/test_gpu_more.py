@@ -312,3 +312,25 @@ def test_frames_download_beside_the_simulation():
         a.synchronize()
     finally:
         L.flk_host_free(p_id); L.flk_host_free(p_rec)
+
+
+@pytest.mark.parametrize("relax", [True, False])
+def test_window_plus_one_switch_matches_the_restatement(relax):
+    """[EXT] E3 of SURVEY.md §8c: if the real engine followed MASON (window = floor(dist/d) + 1 cells on either side),
+    flk_set_engine_semantics(window_plus1=1) is the one switch to flip; the restatement carries the same switch"""
+    from examples_b200 import Real2D
+    W = 160.0
+    birds = make(2500, W, W, seed=4)
+    f = gpu(birds, W, W, relax=relax)
+    f.set_engine_semantics(window_plus1=True)
+    sim = O.Sim(W, W, cfg=O.default_cfg(relax=int(relax), window_plus1=1))
+    sim.init(birds)
+    for t in range(5):
+        sim.step()
+        f.run(t, 1)
+        assert bits_equal(state(f), sim.agents()), (relax, t)
+    for (x, y) in [(80.0, 80.0), (0.3, 159.9)]:
+        got = f.get_neighbors_within_relax_distance(Real2D(x, y), 10.0) if relax else f.get_neighbors_within_distance(Real2D(x, y), 10.0)
+        assert np.array_equal(got, sim.field.neighbors(x, y, 10.0, relax=relax, plus1=True)["id"])
+    f.set_engine_semantics(window_plus1=False)
+    assert len(f.get_neighbors_within_relax_distance(Real2D(80.0, 80.0), 10.0)) < len(sim.field.neighbors(80.0, 80.0, 10.0, plus1=True))
