@@ -103,3 +103,11 @@ def test_balance_columns_is_host_side_and_balanced(lib):
     assert np.abs(np.diff(balanced_columns(u, W, 5)) - mx / 5).max() <= 3
     out = (C.c_int32 * 200)()
     assert lib.load().flk_balance_columns(u.ctypes.data_as(C.c_void_p), u.size, 1, W, 6.6666665, 100, out) < 0
+
+
+def test_rust_shim_declares_every_export():
+    """rust/src/ffi.rs (source only: no cargo in this image) binds exactly the symbols include/flk.h declares"""
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    have = sorted(set(re.findall(r"pub fn (flk_[a-z0-9_]+)", ffi)))
+    assert have == declared_symbols()
+    assert "pub struct flk_bird" in ffi and "#[repr(C)]" in ffi
