@@ -7,7 +7,7 @@ from examples_b200 import Field2D
 
 name = sys.argv[1]
 ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 14
-gx, gy, n, _ = bench.workload_geometry(name, 1, None)
+gx, gy, n, _ = (15, 15, 1000, "") if name == "shipped" else bench.workload_geometry(name, 1, None)
 W, H = bench.field_size(gx), bench.field_size(gy)
 loc = bench.make_birds(n, W, H, name == "clustered")
 f = Field2D(W, H, bench.D, True, capacity=int(n * 1.25) + 65536)
