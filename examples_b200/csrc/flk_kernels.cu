@@ -437,9 +437,140 @@ void launch_step_bands(const Geom &g, const Params &p, const Store &s, const Ste
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_step_warp: Bird::step with ONE WARP PER BIRD, for fields too small to fill the GPU with a thread per bird (the
+// shipped run: 1000 birds = 8 CTAs of k_step, one warp per scheduler, ~8 000 dependent instructions each: 32 us).
+// The lanes share the bird's candidates: every window run is taken 32 candidates at a time, each lane computes the pair
+// terms of one candidate (bird.rs:54-61: toroidal distances, square, the two exact quotients) and parks them in shared
+// memory; then six lanes — one per accumulator of bird.rs:44-49 — add the parked terms in candidate order, so every f32
+// sum is evaluated in exactly the order of the thread-per-bird kernels.  Lane 0 finishes the bird.  Any window width,
+// either query, seam or not, strips too (rows not split).
+// ------------------------------------------------------------------------------------------------
+constexpr int WARP_RUNS = 32;   // window runs a warp keeps in shared memory (3 or 9 for the shipped 3x3 window; 49 for 7x7 -> general kernel)
+
+template <bool RELAX, int MATH>
+__global__ void __launch_bounds__(128) k_step_warp(const __grid_constant__ Geom g, const __grid_constant__ Params p,
+                                                   const __grid_constant__ Store s, const __grid_constant__ StepArgs a) {
+    __shared__ float term_s[4][6][32];
+    __shared__ uint32_t run_s[4][2][WARP_RUNS + 1];        // [0]: first READ index of each run, [1]: candidates before it
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float (*term)[32] = term_s[wid];
+    uint32_t *run_start = run_s[wid][0], *run_pre = run_s[wid][1];
+    const uint32_t lo = a.cell_lo ? __ldg(s.cell_start + a.cell_lo) : 0u;
+    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && hi - lo > gridDim.x * 4u) atomicOr(s.err_flag, ERR_EXCHANGE);
+    const uint32_t i = lo + blockIdx.x * 4u + (uint32_t)wid;
+    if (i >= hi) return;                                   // warp-uniform
+    const uint32_t w = a.out_base + i;
+    const Rec me = s.rec[i];
+    const uint32_t my_id = s.ids[i];
+    const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
+    const Recip Rd = make_recip(g.d);
+    const int gcx = cell_coord(me.x, g.d, g.mx + 1);
+    const int cy = cell_coord(me.y, g.d, g.dh);
+    const int lc = local_col(g, gcx);
+    if (g.mode != 0 && (lc == 0 || lc == g.nown + 1)) {    // ghost copy: stepped by its owner, dropped here
+        if (lane == 0 && !s.slotw) s.tkey[w] = KEY_INVALID;
+        return;
+    }
+    if (a.identity) {                                      // dist commit: re-stage the bird unchanged
+        if (lane == 0) emit_successor<false, 0>(g, s, me, my_id, w, d_ok, Rd, i);
+        return;
+    }
+    const float W = g.W, H = g.H;
+    const float halfW = __fdiv_rn(W, 2.0f), halfH = __fdiv_rn(H, 2.0f);
+    float acc_l = 0.0f;                                    // lanes 0..5: x_avoid, y_avoid, x_cohe, y_cohe, x_cons, y_cons
+    uint32_t nvec = 0;
+    int count = 0;
+    const float4 *__restrict__ rec = reinterpret_cast<const float4 *>(s.rec);
+    if (p.radius > 0.0f) {                                 // both queries return nothing for dist <= 0
+        // ---- the window's runs in query order (all their bounds are requested before any is used)
+        int nruns = 0;
+        uint32_t total = 0;
+        for_each_window_run<0>(g, s.cell_start, lc, cy, p.k, [&](uint32_t rs, uint32_t re) {
+            if (lane == 0 && nruns < WARP_RUNS) { run_start[nruns] = rs; run_pre[nruns] = total; }
+            total += re - rs;
+            ++nruns;
+        });
+        if (lane == 0 && nruns <= WARP_RUNS) run_pre[nruns] = total;
+        __syncwarp();
+        // ---- candidates 32 at a time, by their position in the query result
+        for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+            const uint32_t c = c0 + (uint32_t)lane;
+            bool keep = c < total;
+            bool self = false;
+            if (keep) {
+                int r = 0;
+                for (int q = 1; q < nruns; ++q) r += run_pre[q] <= c ? 1 : 0;     // the run that holds candidate c
+                const uint32_t j = run_start[r] + (c - run_pre[r]);
+                self = j == i;                                                     // bird.rs:53
+                const float4 o = __ldg(rec + j);
+                const float dx = toroidal_distance(me.x, o.x, W, halfW);           // bird.rs:54
+                const float dy = toroidal_distance(me.y, o.y, H, halfH);           // bird.rs:55
+                const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));  // :59
+                if (!RELAX) {   // get_neighbors_within_distance keeps elem iff sqrt(dx^2+dy^2) <= dist
+                    float qs = sq;
+                    if (!g.toroidal) {
+                        const float px = __fadd_rn(me.x, -o.x), py = __fadd_rn(me.y, -o.y);
+                        qs = __fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py));
+                    }
+                    keep = __fsqrt_rn(qs) <= p.radius;
+                }
+                const float den = __fadd_rn(__fmul_rn(sq, sq), 1.0f);
+                float qa, qb;
+                if (MATH == 0) {
+                    div2_rn(dx, dy, den, qa, qb);          // :60-61, two IEEE divisions
+                } else {
+                    float inv;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+                    qa = __fmul_rn(dx, inv);
+                    qb = __fmul_rn(dy, inv);
+                }
+                term[0][lane] = qa; term[1][lane] = qb;       // :60-61
+                term[2][lane] = dx; term[3][lane] = dy;       // :64-65
+                term[4][lane] = o.z; term[5][lane] = o.w;     // :68-69
+            }
+            const uint32_t kept = __ballot_sync(0xffffffffu, keep);
+            const uint32_t add = kept & ~__ballot_sync(0xffffffffu, self);
+            nvec += (uint32_t)__popc(kept);
+            count += __popc(add);                          // :56
+            __syncwarp();
+            if (lane < 6) {
+                uint32_t m = add;
+                while (m) {                                // candidates in order, one rounded addition each
+                    const int e = __ffs(m) - 1;
+                    m &= m - 1;
+                    acc_l = __fadd_rn(acc_l, term[lane][e]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    Acc acc;
+    acc.xa = __shfl_sync(0xffffffffu, acc_l, 0); acc.ya = __shfl_sync(0xffffffffu, acc_l, 1);
+    acc.xc = __shfl_sync(0xffffffffu, acc_l, 2); acc.yc = __shfl_sync(0xffffffffu, acc_l, 3);
+    acc.xs = __shfl_sync(0xffffffffu, acc_l, 4); acc.ys = __shfl_sync(0xffffffffu, acc_l, 5);
+    acc.nvec = nvec; acc.count = count;
+    if (lane == 0) finish_bird<MATH, false, 0>(g, p, s, a, me, my_id, w, acc, d_ok, Rd, i);
+}
+
+constexpr uint32_t WARP_STEP_MAX = 12288;   // birds: up to here a warp per bird beats a thread per bird (B200: crossover ~15 000)
+
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st) {
     if (n_upper == 0) return;
+    static const uint32_t warp_max = [] { const char *e = getenv("FLK_STEP_WARP"); return e ? (uint32_t)atoi(e) : WARP_STEP_MAX; }();   // A/B runs
+    if (n_upper <= warp_max && g.mode != 2 && (2 * p.k + 1) * (2 * p.k + 1) <= WARP_RUNS) {
+        const dim3 blk(128), grd((n_upper + 3) / 4);
+        if (p.relax) {
+            if (a.math_mode == 1) k_step_warp<true, 1><<<grd, blk, 0, st>>>(g, p, s, a);
+            else k_step_warp<true, 0><<<grd, blk, 0, st>>>(g, p, s, a);
+        } else {
+            if (a.math_mode == 1) k_step_warp<false, 1><<<grd, blk, 0, st>>>(g, p, s, a);
+            else k_step_warp<false, 0><<<grd, blk, 0, st>>>(g, p, s, a);
+        }
+        return;
+    }
     static const int tile = [] { const char *e = getenv("FLK_STEP_TILE"); return e ? atoi(e) : 1; }();
     const int bs = FLK_STEP_BS;
     const dim3 block(bs), grid((n_upper + bs - 1) / bs);

@@ -9,6 +9,9 @@ names = sys.argv[1:] or ["shipped", "1m", "weak16m"]
 for name in names:
     if name == "shipped":
         gx = gy = 15; n = 1000
+    elif name.startswith("n"):           # n<birds>: a square field of the shipped density
+        n = int(name[1:])
+        gx = gy = max(int(round((n / 0.0996) ** 0.5 / bench.D)), 6)
     else:
         gx, gy, n, _ = bench.workload_geometry(name, 1, None)
     W, H = bench.field_size(gx), bench.field_size(gy)
