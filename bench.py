@@ -50,6 +50,8 @@ def workload_geometry(name: str, world: int, birds_per_gpu: int | None):
     if name == "clustered":
         per = birds_per_gpu or 16_000_000
         return 672 * world, 5376, per * world, f"flockers clustered flocks, {per} birds/GPU, {672 * world}x5376 cells"
+    if name == "shipped":
+        return 15, 15, 1000, "flockers as shipped: 1000 birds, 100x100 field = 15x15 cells (flockers/src/main.rs:40-44)"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -372,12 +374,13 @@ def run_ours(args, world: int, rank: int, local_rank: int):
         return dict(f=f, W=W, H=H, gx=gx, gy=gy, n_total=n_total, n_local=n_local, cap=cap, loc=loc, id_base=id_base,
                     label=label, clustered=clustered)
 
-    def timed_run(f, n_total, first, warmup, steps, sampler=None):
-        """W warm-up ticks, then K ticks timed on the device (CUDA events on the handle's stream, max over ranks)"""
+    def timed_run(f, n_total, first, warmup, steps, sampler=None, profile=True):
+        """W warm-up ticks, then K ticks timed on the device (CUDA events on the handle's stream, max over ranks).
+        profile: CUDA events around every k_step launch of the timed region (plain launches instead of graph replays)"""
         f.run(first, warmup, STEP_SEED)
         f.synchronize()
         launches0 = f.launch_count()
-        f.profile_enable(1)   # CUDA events around every k_step launch of the timed region
+        f.profile_enable(1 if profile else 0)
         if sampler is not None:
             sampler.start()
         barrier()
@@ -529,14 +532,15 @@ def run_ours(args, world: int, rank: int, local_rank: int):
     # ---- the other BASELINE configs, short legs (driver-visible numbers for configs 2, 3 and 5) ----
     extras = {}
     if not args.no_extras and args.workload == "weak16m" and args.birds_per_gpu is None:
-        legs = [("1m", 200), ("clustered", 10)] if world == 1 else [("strong16m", 100)]
+        legs = [("shipped", 2000), ("1m", 200), ("clustered", 10)] if world == 1 else [("strong16m", 100)]
         for name, k in legs:
             try:
                 w2 = build_field(name, None)
-                r2 = timed_run(w2["f"], w2["n_total"], 0, 10, k)
+                r2 = timed_run(w2["f"], w2["n_total"], 0, 10, k, profile=False)     # the way flk_run runs: graph replays
+                r3 = timed_run(w2["f"], w2["n_total"], 10 + k, 0, min(k, 20))       # a few more ticks with k_step events
                 extras[name] = {"value": r2["value"], "unit": "bird-updates/s", "ms_per_step": r2["ms"] / k, "steps": k,
                                 "warmup": 10, "workload": w2["label"], "birds_after": int(sum_over_ranks(float(w2["f"].num_owned()))),
-                                "k_step_ms": max_over_ranks(r2["k_ms"] / max(r2["k_n"], 1))}
+                                "k_step_ms": max_over_ranks(r3["k_ms"] / max(r3["k_n"], 1))}
                 w2["f"].close()
             except Exception as e:   # an extra leg never takes the headline down with it
                 extras[name] = {"error": repr(e)}
@@ -675,7 +679,7 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="weak16m", choices=["weak16m", "strong16m", "1m", "clustered"])
+    ap.add_argument("--workload", default="weak16m", choices=["weak16m", "strong16m", "1m", "clustered", "shipped"])
     ap.add_argument("--birds-per-gpu", type=int, default=None)
     ap.add_argument("--math", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=1)   # > 1: split the rows too (tiles); default = x-strips
