@@ -48,6 +48,10 @@ int field_alloc(flk_field *f) {
     s.stage = reinterpret_cast<uint4 *>(f->scratch);
     const uint64_t nblk = (m + 2047) / 2048 + 1;
     CUDA_TRY(cudaMalloc(&s.blocksum, nblk * 4));
+    if (f->g.mode == 0) {   // column-aligned k_step launches (single-GPU handles)
+        CUDA_TRY(cudaMalloc(&s.colchunk, ((uint64_t)f->g.ncols + 1) * 4));
+        CUDA_TRY(cudaMemsetAsync(s.colchunk, 0, ((uint64_t)f->g.ncols + 1) * 4, f->stream));
+    }
     CUDA_TRY(cudaMalloc(&s.step_dev, 8));
     CUDA_TRY(cudaMalloc(&s.n_read_dev, 4));
     CUDA_TRY(cudaMalloc(&s.err_flag, 4));
@@ -256,6 +260,7 @@ void field_free(flk_field *f) {
     cudaFree(s.rec); cudaFree(s.ids); cudaFree(s.cell_start); cudaFree(s.trec); cudaFree(s.tid);
     cudaFree(s.tkey); cudaFree(s.tslot); cudaFree(s.cnt); cudaFree(f->scratch); cudaFree(s.blocksum);
     cudaFree(s.step_dev); cudaFree(s.n_read_dev); cudaFree(s.err_flag);
+    if (s.colchunk) cudaFree(s.colchunk);
     if (s.pay) cudaFree(s.pay);
     if (s.tpay) cudaFree(s.tpay);
     if (f->d_paystage) cudaFree(f->d_paystage);
@@ -382,7 +387,7 @@ int enqueue_lazy_update(flk_field *f, int bump_step) {
         launch_scan(f->s, m, f->stream);
         if (int rc = mark()) return rc;
         CUDA_TRY(cudaMemsetAsync(f->s.sw_totals, 0, 8, f->stream));
-        launch_compact(f->s, f->ncell, bump_step, f->stream);
+        launch_compact(f->s, f->ncell, bump_step, f->stream, (uint32_t)f->g.ncols, (uint32_t)f->g.dh);
         CUDA_TRY(cudaMemsetAsync(f->s.sw_spill_cnt, 0, 4, f->stream));
         if (int rc = mark()) return rc;
         if (int rc = mark()) return rc;
@@ -405,7 +410,7 @@ int enqueue_lazy_update(flk_field *f, int bump_step) {
     if (int rc = mark()) return rc;
     launch_scatter(f->s, (uint32_t)f->w_count, f->g.mode != 0, f->stream);
     if (int rc = mark()) return rc;
-    launch_rank(f->s, (uint32_t)f->w_count, f->ncell, bump_step, f->stream);
+    launch_rank(f->s, (uint32_t)f->w_count, f->ncell, bump_step, f->stream, (uint32_t)f->g.ncols, (uint32_t)f->g.dh);
     if (int rc = mark()) return rc;
     f->launches += 3 + (f->g.mode != 0 ? 2 : (f->w_count ? 1 : 0)) + 1;
     CUDA_TRY(cudaGetLastError());
@@ -430,6 +435,7 @@ int enqueue_step(flk_field *f, uint64_t step, int use_step_dev, uint64_t seed, c
     a.math_mode = f->math_mode;
     a.identity = 0;
     a.skip_bands = 0;
+    a.nseam = 0;
     const bool prof = f->profile && !f->capturing;
     if (prof) {
         cudaEvent_t e0, e1;

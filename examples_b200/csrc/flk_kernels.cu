@@ -288,7 +288,13 @@ __device__ __noinline__ void step_bird_general(const Geom &g, const Params &p, c
 #define FLK_STEP_MINBLOCKS 9   // 56 registers; with the prefetching loop: 0.851 ms (9), 0.856 (10), 0.884 (12)
 #endif
 // TILES = the rows are split too (mode 2): the row of the local cell arrays differs from the global row
-template <bool RELAX, int MATH, bool TILE, bool FASTG, bool TILES = false>
+// COLS (single-GPU handles, with TILE and FASTG): the grid is aligned to the cell columns.  After the a.nseam seam CTAs, CTA
+// b steps one chunk of FLK_STEP_BS birds of ONE column (s.colchunk maps chunks to columns), so no CTA straddles two
+// columns, and a CTA that starts or ends a column stages the rows it has (clamped at the seam) instead of leaving the tile
+// path: the birds of the seam rows 0, my-1 and my (slack) of such a column need the full toroidal distance and are stepped
+// by the seam CTAs at the head of the grid, one warp per seam cell.  The chunks of the last two columns (x seam and slack:
+// general path, several times slower per CTA) are taken first as well, so that no slow CTA starts in the last wave.
+template <bool RELAX, int MATH, bool TILE, bool FASTG, bool TILES = false, bool COLS = false>
 __global__ void __launch_bounds__(FLK_STEP_BS, FLK_STEP_MINBLOCKS)
 k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const __grid_constant__ Store s,
        const __grid_constant__ StepArgs a) {
@@ -299,14 +305,43 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
 
     // cell_start[0] is 0 by construction: a whole-field launch knows its first bird without a load, so the bird's own
     // record (read speculatively: any index below cap is allocated) is in flight together with the range end
-    const uint32_t lo = a.cell_lo ? __ldg(s.cell_start + a.cell_lo) : 0u;
-    const uint32_t first = lo + blockIdx.x * blockDim.x;
+    uint32_t lo, hi, first;
+    if (COLS) {
+        const uint32_t dhc = (uint32_t)g.dh;
+        if (blockIdx.x < a.nseam) {
+            // ---- seam rows of the tile columns: one warp per cell (rows 0, my-1, my of columns 1 .. mx-2)
+            const uint32_t wq = blockIdx.x * (FLK_STEP_BS / 32) + (threadIdx.x >> 5);
+            const uint32_t c = 1u + wq / 3u, k3 = wq % 3u;
+            if ((int)c > g.mx - 2) return;
+            const uint32_t row = k3 == 0 ? 0u : (k3 == 1 ? (uint32_t)g.my - 1u : (uint32_t)g.my);
+            const uint32_t b0 = __ldg(s.cell_start + c * dhc + row), b1 = __ldg(s.cell_start + c * dhc + row + 1);
+            for (uint32_t q = b0 + (threadIdx.x & 31u); q < b1; q += 32) step_bird_general<RELAX, MATH, TILES>(g, p, s, a, q, a.out_base + q);
+            return;
+        }
+        const uint32_t ncols = (uint32_t)g.ncols, nch = __ldg(s.colchunk + ncols);
+        uint32_t B = blockIdx.x - a.nseam;
+        if (B >= nch) return;
+        // the chunks of the last two columns first (see above), then columns 0 .. mx-2 in order
+        const uint32_t tailc = nch - __ldg(s.colchunk + ncols - 2);
+        B = B < tailc ? nch - tailc + B : B - tailc;
+        uint32_t c = min(ncols - 1, (uint32_t)(((uint64_t)B * ncols) / nch));
+        while (__ldg(s.colchunk + c) > B) --c;
+        while (__ldg(s.colchunk + c + 1) <= B) ++c;
+        lo = __ldg(s.cell_start + c * dhc);
+        hi = __ldg(s.cell_start + (c + 1) * dhc);
+        first = lo + (B - __ldg(s.colchunk + c)) * blockDim.x;
+    } else {
+        lo = a.cell_lo ? __ldg(s.cell_start + a.cell_lo) : 0u;
+        first = lo + blockIdx.x * blockDim.x;
+    }
     const uint32_t i = first + threadIdx.x;
     float2 xy = make_float2(0.0f, 0.0f);
     if (TILE && i < s.cap) xy = *reinterpret_cast<const float2 *>(s.rec + i);
-    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && hi - lo > gridDim.x * blockDim.x)
-        atomicOr(s.err_flag, ERR_EXCHANGE);        // the launch does not cover the range (border launches use capx)
+    if (!COLS) {
+        hi = __ldg(s.cell_start + a.cell_hi);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && hi - lo > gridDim.x * blockDim.x)
+            atomicOr(s.err_flag, ERR_EXCHANGE);    // the launch does not cover the range (border launches use capx)
+    }
     if (first >= hi) return;                       // whole CTA out of range
     const bool valid = i < hi;
     const uint32_t w = a.out_base + i;
@@ -335,15 +370,17 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
         __syncthreads();
         const int lcA = shc[0], cyA = shc[1], lcB = shc[2], cyB = shc[3], gcxA = shc[4];
         const int lrA = TILES ? shc[5] : cyA, lrB = TILES ? shc[6] : cyB;
+        // COLS: the seam rows are somebody else's, so any row range of a tile column will do (staged rows clamped to 0 .. my-1)
         bool eligible = (FASTG || (RELAX && !a.identity && g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && d_ok &&
                                    s.pw == 0)) &&
-                        lcA == lcB && gcxA >= 1 && gcxA <= g.mx - 2 && cyA >= 1 && cyB <= g.my - 2 && cyA <= cyB &&
+                        lcA == lcB && gcxA >= 1 && gcxA <= g.mx - 2 && (COLS || (cyA >= 1 && cyB <= g.my - 2)) && cyA <= cyB &&
                         (g.mode == 0 || (lcA >= 1 && lcA <= g.nown)) &&
                         (!TILES || (lrA >= 1 && lrB <= g.rown && lrA <= lrB));
         uint32_t sA0 = 0, sA1 = 0, sA2 = 0, len0 = 0, len1 = 0, len2 = 0;
         if (eligible) {
-            const uint32_t *cs = s.cell_start + ((uint32_t)(lcA - 1) * dh + (uint32_t)(lrA - 1));
-            const uint32_t span = (uint32_t)(lrB - lrA) + 3u;
+            const int rlo = COLS ? max(lrA - 1, 0) : lrA - 1, rhi = COLS ? min(lrB + 1, g.my - 1) : lrB + 1;
+            const uint32_t *cs = s.cell_start + ((uint32_t)(lcA - 1) * dh + (uint32_t)rlo);
+            const uint32_t span = (uint32_t)(rhi - rlo) + 1u;
             sA0 = __ldg(cs);          len0 = __ldg(cs + span) - sA0;
             sA1 = __ldg(cs + dh);     len1 = __ldg(cs + dh + span) - sA1;
             sA2 = __ldg(cs + 2 * dh); len2 = __ldg(cs + 2 * dh + span) - sA2;
@@ -359,7 +396,7 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
             }
             // this bird's three runs, as offsets into the staged column runs (loads in flight during the copy)
             uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0, a2 = 0, b2 = 0;
-            if (valid) {
+            if (valid && !(COLS && (cy == 0 || cy >= g.my - 1))) {
                 const uint32_t *cs = s.cell_start + ((uint32_t)(lc - 1) * dh + (uint32_t)(lr - 1));
                 a0 = __ldg(cs);          b0 = __ldg(cs + 3);
                 a1 = __ldg(cs + dh);     b1 = __ldg(cs + dh + 3);
@@ -367,6 +404,7 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
             }
             mbar_wait(&bar, 0);
             if (!valid) return;
+            if (COLS && (cy == 0 || cy >= g.my - 1)) return;                       // a seam row: stepped by the seam CTAs
             if (TILES && a.skip_bands && (lr <= 2 || lr >= g.rown - 1)) return;   // stepped by k_step_bands
             float xa = 0.0f, ya = 0.0f, xc = 0.0f, yc = 0.0f, xs = 0.0f, ys = 0.0f;
             if (MATH == 0 && FLK_PACKED) {
@@ -394,6 +432,11 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
         }
     }
     if (!valid) return;
+    if (COLS) {   // a tile column's seam-row birds belong to the seam CTAs whatever path this CTA takes
+        const Rec me = s.rec[i];
+        const int cx = cell_coord(me.x, g.d, g.mx + 1), cy = cell_coord(me.y, g.d, g.dh);
+        if (cx >= 1 && cx <= g.mx - 2 && (cy == 0 || cy >= g.my - 1)) return;
+    }
     if (g.mode != 0) {
         const Rec me = s.rec[i];
         const int lc = local_col(g, cell_coord(me.x, g.d, g.mx + 1));
@@ -554,6 +597,7 @@ __global__ void __launch_bounds__(128) k_step_warp(const __grid_constant__ Geom 
     if (lane == 0) finish_bird<MATH, false, 0>(g, p, s, a, me, my_id, w, acc, d_ok, Rd, i);
 }
 
+constexpr uint32_t COLS_STEP_MAX = 4000000;   // birds: up to here the column-aligned grid pays (fewer waves: a slow CTA in the last wave is a visible tail)
 constexpr uint32_t WARP_STEP_MAX = 12288;   // birds: up to here a warp per bird beats a thread per bird (B200: crossover ~15 000)
 
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
@@ -572,10 +616,19 @@ void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs 
         return;
     }
     static const int tile = [] { const char *e = getenv("FLK_STEP_TILE"); return e ? atoi(e) : 1; }();
+    static const uint32_t colgrid_max = [] { const char *e = getenv("FLK_STEP_COLS"); return e ? (uint32_t)atoi(e) : COLS_STEP_MAX; }();   // A/B runs
     const int bs = FLK_STEP_BS;
     const dim3 block(bs), grid((n_upper + bs - 1) / bs);
     const bool fastg = p.relax && g.toroidal && p.k == 1 && g.mx >= 6 && g.my >= 6 && g.d >= 0x1p-20f && g.d <= 4096.0f &&
                        s.pw == 0 && !a.identity;
+    // single-GPU handles of moderate size: column-aligned grid + seam CTAs (whole-field launches only)
+    if (g.mode == 0 && tile && fastg && n_upper <= colgrid_max && s.colchunk && a.cell_lo == 0 && a.math_mode == 0) {
+        StepArgs ac = a;
+        ac.nseam = (3u * (uint32_t)(g.mx - 2) + bs / 32 - 1) / (bs / 32);
+        const dim3 gridc(ac.nseam + (n_upper + bs - 1) / bs + (uint32_t)g.ncols);   // every column ends with one partial chunk at most
+        k_step<true, 0, true, true, false, true><<<gridc, block, 0, st>>>(g, p, s, ac);
+        return;
+    }
 #define FLK_LAUNCH(R, M, T, F) k_step<R, M, T, F><<<grid, block, 0, st>>>(g, p, s, a)
 #define FLK_LAUNCH_T(R, M, T) k_step<R, M, T, false, true><<<grid, block, 0, st>>>(g, p, s, a)
     if (g.mode == 2) {   // rows split: every variant is the TILES instantiation (ghost rows, local row arithmetic)
@@ -899,12 +952,36 @@ void launch_scatter(const Store &s, uint32_t n, int dist, cudaStream_t st) {
     k_scatter4<<<((n + FLK_SCATTER_E - 1) / FLK_SCATTER_E + 255) / 256, 256, 0, st>>>(s, n, 0);
 }
 
+// colchunk[c] = k_step CTAs needed by the columns before c (column-aligned launches); one CTA, after cell_start is final
+__device__ __forceinline__ void build_colchunk(const Store &s, uint32_t ncols, uint32_t dh) {
+    __shared__ uint32_t sh_carry;
+    if (threadIdx.x == 0) sh_carry = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < ncols; c0 += blockDim.x) {
+        const uint32_t c = c0 + threadIdx.x;
+        uint32_t ch = 0;
+        if (c < ncols) ch = (s.cell_start[(c + 1) * dh] - s.cell_start[c * dh] + FLK_STEP_BS - 1) / FLK_STEP_BS;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan<256>(ch, &total);
+        if (c < ncols) s.colchunk[c] = sh_carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) sh_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s.colchunk[ncols] = sh_carry;
+}
+
 // two staged entries per thread: both record gathers and both cell-range loads are in flight before either member
 // loop starts (the one-entry form ran at 61 % of DRAM bandwidth)
 #ifndef FLK_RANK_MINBLOCKS
 #define FLK_RANK_MINBLOCKS 8   // 32 registers, full occupancy: 0.138 ms against 0.148 (6 CTAs/SM) and 0.158 (4-5)
 #endif
-__global__ void __launch_bounds__(256, FLK_RANK_MINBLOCKS) k_rank(const Store s, uint32_t ncell, int bump_step) {
+__global__ void __launch_bounds__(256, FLK_RANK_MINBLOCKS) k_rank(const Store s, uint32_t ncell, int bump_step, uint32_t ncols,
+                                                                  uint32_t dh) {
+    if (blockIdx.x == gridDim.x - 1 && ncols) {   // an extra CTA at the end of the grid
+        build_colchunk(s, ncols, dh);
+        return;
+    }
     const uint32_t n = min(s.cell_start[ncell], s.cap);
     const uint32_t p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 2u;
     if (p0 == 0) {
@@ -942,9 +1019,10 @@ __global__ void __launch_bounds__(256, FLK_RANK_MINBLOCKS) k_rank(const Store s,
     }
 }
 
-void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st) {
+void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st, uint32_t ncols, uint32_t dh) {
     const uint32_t nb = n_upper == 0 ? 1 : ((n_upper + 1) / 2 + 255) / 256;
-    k_rank<<<nb, 256, 0, st>>>(s, ncell, bump_step);
+    if (!s.colchunk) ncols = 0;
+    k_rank<<<nb + (ncols ? 1 : 0), 256, 0, st>>>(s, ncell, bump_step, ncols, dh);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -989,7 +1067,12 @@ __device__ __noinline__ void compact_spilled_cell(const Store &s, uint32_t cell,
 
 // (__grid_constant__: the out-of-line spill merge takes the store by reference; without it every thread would first copy
 // the whole parameter struct to its stack)
-__global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Store s, uint32_t ncell, int bump_step) {
+__global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Store s, uint32_t ncell, int bump_step, uint32_t ncols,
+                                                 uint32_t dh) {
+    if (blockIdx.x == gridDim.x - 1 && ncols) {   // an extra CTA at the end of the grid
+        build_colchunk(s, ncols, dh);
+        return;
+    }
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t cell = gid >> 3, l8 = gid & 7u;
     const int lane = threadIdx.x & 31, grp = lane & 24;
@@ -1053,9 +1136,10 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Store s
     if (spilled && l8 == 0) compact_spilled_cell(s, cell, cs, n);
 }
 
-void launch_compact(const Store &s, uint32_t ncell, int bump_step, cudaStream_t st) {
+void launch_compact(const Store &s, uint32_t ncell, int bump_step, cudaStream_t st, uint32_t ncols, uint32_t dh) {
     const uint64_t threads = (uint64_t)ncell * 8;
-    k_compact<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(s, ncell, bump_step);
+    if (!s.colchunk) ncols = 0;
+    k_compact<<<(unsigned)((threads + 255) / 256) + (ncols ? 1 : 0), 256, 0, st>>>(s, ncell, bump_step, ncols, dh);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -50,6 +50,9 @@ struct Store {
     uint32_t *sw_spill_cnt;
     uint32_t sw_spill_cap;
     uint32_t *sw_totals;   // [2] of the last k_compact: largest cell, spilled arrivals
+    // single-GPU handles: colchunk[c] = number of k_step CTAs (chunks of FLK_STEP_BS birds) that the columns before c need,
+    // colchunk[ncols] = all of them (written with cell_start by lazy_update: k_rank / k_compact); null = not maintained
+    uint32_t *colchunk;
 };
 
 constexpr uint32_t ERR_CAPACITY = 1u;   // more objects than `cap` after an exchange
@@ -79,6 +82,7 @@ struct StepArgs {
     int math_mode;              // 0 exact, 1 fast
     int identity;               // 1 = re-stage every owned bird unchanged (dist commit: builds the first halo)
     int skip_bands;             // tiles: the two owned rows next to each row boundary are stepped by k_step_bands, skip them
+    uint32_t nseam;             // column-aligned launches (COLS): CTAs at the head of the grid that step the seam-row cells
 };
 
 void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id, const float2 *loc,
@@ -102,9 +106,9 @@ void launch_step_bands(const Geom &g, const Params &p, const Store &s, const Ste
 // exclusive scan of cnt -> cell_start, zeroing cnt; 3 launches
 void launch_scan(const Store &s, uint32_t ncell_plus1, cudaStream_t st);
 void launch_scatter(const Store &s, uint32_t n_write_extent, int dist, cudaStream_t st);
-void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st);
+void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st, uint32_t ncols = 0, uint32_t dh = 0);
 // slot-staged WRITE buffer -> READ buffer in (cell, ascending id) order, given cell_start (one pass, 8 lanes per cell)
-void launch_compact(const Store &s, uint32_t ncell, int bump_step, cudaStream_t st);
+void launch_compact(const Store &s, uint32_t ncell, int bump_step, cudaStream_t st, uint32_t ncols = 0, uint32_t dh = 0);
 void launch_selftest_div2(uint64_t n, uint64_t seed, unsigned long long *mismatches, cudaStream_t st);
 void launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t st);
 void launch_find(const Store &s, uint32_t n_upper, uint32_t id, float4 *out, uint32_t *found, cudaStream_t st);

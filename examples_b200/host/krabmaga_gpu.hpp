@@ -55,8 +55,23 @@ public:
     void set_object_location(const Bird &b, Real2D loc) {
         check(flk_set_object_location(h_, b.id, loc.x, loc.y, b.last_d.x, b.last_d.y));
     }
-    std::vector<uint32_t> get_neighbors_within_relax_distance(Real2D loc, float dist) { return query(loc, dist, true); }
-    std::vector<uint32_t> get_neighbors_within_distance(Real2D loc, float dist) { return query(loc, dist, false); }
+    // like the reference (bird.rs:29-31): the objects themselves, in query order — Bird::step reads elem.loc / elem.last_d
+    std::vector<Bird> get_neighbors_within_relax_distance(Real2D loc, float dist) { return query(loc, dist, true); }
+    std::vector<Bird> get_neighbors_within_distance(Real2D loc, float dist) { return query(loc, dist, false); }
+    // Field2D::get(&object) / get_location(object) (visualization/vis_state.rs:52, bird_vis.rs:23); false = not in the field
+    bool get(const Bird &b, Bird *out) {
+        float r[4];
+        int32_t found = 0;
+        check(flk_get_object(h_, b.id, r, &found));
+        if (found && out) *out = Bird{b.id, {r[0], r[1]}, {r[2], r[3]}};
+        return found != 0;
+    }
+    bool get_location(const Bird &b, Real2D *loc) {
+        Bird cur;
+        if (!get(b, &cur)) return false;
+        if (loc) *loc = cur.loc;
+        return true;
+    }
     void lazy_update() { check(flk_lazy_update(h_)); }
     void clear() { check(flk_field_clear(h_)); }
     void step_all_birds(uint64_t step, uint64_t seed) { check(flk_step(h_, step, seed, nullptr, 0)); }
@@ -89,16 +104,18 @@ public:
     const float width, height;
 
 private:
-    std::vector<uint32_t> query(Real2D loc, float dist, bool relax) {
-        std::vector<uint32_t> ids(256);
+    std::vector<Bird> query(Real2D loc, float dist, bool relax) {
+        static_assert(sizeof(flk_bird) == sizeof(Bird), "Bird is flk_bird: {id, loc, last_d}");
+        std::vector<Bird> out(256);
         uint32_t n = 0;
         for (;;) {
-            int rc = relax ? flk_get_neighbors_within_relax_distance(h_, loc.x, loc.y, dist, ids.data(), (uint32_t)ids.size(), &n)
-                           : flk_get_neighbors_within_distance(h_, loc.x, loc.y, dist, ids.data(), (uint32_t)ids.size(), &n);
-            if (rc == FLK_E_CAPACITY && n > ids.size()) { ids.resize(n); continue; }
+            flk_bird *p = reinterpret_cast<flk_bird *>(out.data());
+            int rc = relax ? flk_get_neighbors_within_relax_distance_objects(h_, loc.x, loc.y, dist, p, (uint32_t)out.size(), &n)
+                           : flk_get_neighbors_within_distance_objects(h_, loc.x, loc.y, dist, p, (uint32_t)out.size(), &n);
+            if (rc == FLK_E_CAPACITY && n > out.size()) { out.resize(n); continue; }
             check(rc);
-            ids.resize(n);
-            return ids;
+            out.resize(n);
+            return out;
         }
     }
     flk_field *h_ = nullptr;
