@@ -568,7 +568,7 @@ def run_ours(args, world: int, rank: int, local_rank: int):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_step", "kernel_ms": k_avg_ms,
                          "kernel_share_of_step": k_avg_ms / (ms / args.steps), "peak_source": peak_src,
-                         "other_kernels_ms": {"k_scan_x3": rebin_ms[0], "k_scatter": rebin_ms[1], "k_rank": rebin_ms[2]},
+                         "other_kernels_ms": {"k_scan": rebin_ms[0], "k_scatter": rebin_ms[1], "k_rank": rebin_ms[2]},
                          "algorithmic_bytes_per_update": ALGO_BYTES_PER_UPDATE,
                          "issue_slots": issue_roofline(warp_instr, k_avg_ms, sm_count, (clocks or {}).get("sm_mhz")),
                          "note": "path is FP32-issue bound, not HBM bound (DESIGN.md roofline): see issue_slots"},

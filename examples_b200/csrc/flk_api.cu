@@ -36,7 +36,7 @@ int field_alloc(flk_field *f) {
     const uint64_t capw = cap + (uint64_t)s.nrecv * s.capx;   // WRITE slots: stepped/uploaded + received from the neighbours
     CUDA_TRY(cudaMalloc(&s.rec, cap * sizeof(Rec)));
     CUDA_TRY(cudaMalloc(&s.ids, cap * 4));
-    const uint64_t mp = ((m + 2047) / 2048) * 2048;   // padded to the scan tile (k_scan_* use whole-tile vector accesses)
+    const uint64_t mp = ((m + 2047) / 2048) * 2048;   // padded to the scan tile (k_scan_onepass uses whole-tile vector accesses)
     CUDA_TRY(cudaMalloc(&s.cell_start, mp * 4));
     CUDA_TRY(cudaMalloc(&s.trec, capw * sizeof(Rec)));
     CUDA_TRY(cudaMalloc(&s.tid, capw * 4));
@@ -47,7 +47,8 @@ int field_alloc(flk_field *f) {
     CUDA_TRY(cudaMalloc(&f->scratch, cap * 20 + 128));
     s.stage = reinterpret_cast<uint4 *>(f->scratch);
     const uint64_t nblk = (m + 2047) / 2048 + 1;
-    CUDA_TRY(cudaMalloc(&s.blocksum, nblk * 4));
+    CUDA_TRY(cudaMalloc(&s.scan_state, (nblk + 2) * 8));
+    CUDA_TRY(cudaMemsetAsync(s.scan_state, 0, (nblk + 2) * 8, f->stream));
     if (f->g.mode == 0) {   // column-aligned k_step launches (single-GPU handles)
         CUDA_TRY(cudaMalloc(&s.colchunk, ((uint64_t)f->g.ncols + 1) * 4));
         CUDA_TRY(cudaMemsetAsync(s.colchunk, 0, ((uint64_t)f->g.ncols + 1) * 4, f->stream));
@@ -182,7 +183,7 @@ int ensure_view(flk_field *f) {
     CUDA_TRY(cudaMemcpyAsync(f->s.cnt, f->S.cnt[f->S.rd], (uint64_t)f->ncell * 4, cudaMemcpyDeviceToDevice, f->stream));
     launch_scan(f->s, f->ncell + 1, f->stream);            // -> cell_start; leaves s.cnt zeroed again
     launch_slot_materialize(f->g, slot_args(f->S), f->s, f->ncell, f->stream);
-    f->launches += 4;
+    f->launches += 2;
     CUDA_TRY(cudaGetLastError());
     f->view_valid = true;
     return FLK_OK;
@@ -258,7 +259,7 @@ int maybe_promote_to_slots(flk_field *f) {
 void field_free(flk_field *f) {
     Store &s = f->s;
     cudaFree(s.rec); cudaFree(s.ids); cudaFree(s.cell_start); cudaFree(s.trec); cudaFree(s.tid);
-    cudaFree(s.tkey); cudaFree(s.tslot); cudaFree(s.cnt); cudaFree(f->scratch); cudaFree(s.blocksum);
+    cudaFree(s.tkey); cudaFree(s.tslot); cudaFree(s.cnt); cudaFree(f->scratch); cudaFree(s.scan_state);
     cudaFree(s.step_dev); cudaFree(s.n_read_dev); cudaFree(s.err_flag);
     if (s.colchunk) cudaFree(s.colchunk);
     if (s.pay) cudaFree(s.pay);
@@ -392,7 +393,7 @@ int enqueue_lazy_update(flk_field *f, int bump_step) {
         if (int rc = mark()) return rc;
         if (int rc = mark()) return rc;
         CUDA_TRY(cudaMemcpyAsync(f->h_sw, f->s.sw_totals, 8, cudaMemcpyDeviceToHost, f->stream));
-        f->launches += 4;
+        f->launches += 2;
         CUDA_TRY(cudaGetLastError());
         f->n_read = f->w_count;
         f->w_count = 0;
@@ -405,14 +406,26 @@ int enqueue_lazy_update(flk_field *f, int bump_step) {
         if (!f->capturing && !f->layout_forced && f->h_sw[1] > limit) return set_slotw(f, 0);
         return FLK_OK;
     }
-    if (int rc = mark()) return rc;
-    launch_scan(f->s, m, f->stream);
-    if (int rc = mark()) return rc;
-    launch_scatter(f->s, (uint32_t)f->w_count, f->g.mode != 0, f->stream);
-    if (int rc = mark()) return rc;
-    launch_rank(f->s, (uint32_t)f->w_count, f->ncell, bump_step, f->stream, (uint32_t)f->g.ncols, (uint32_t)f->g.dh);
-    if (int rc = mark()) return rc;
-    f->launches += 3 + (f->g.mode != 0 ? 2 : (f->w_count ? 1 : 0)) + 1;
+    static const uint64_t small_max = [] {
+        const char *e = getenv("FLK_REBIN_SMALL");
+        return e ? strtoull(e, nullptr, 10) : (uint64_t)SMALL_REBIN_MAX;
+    }();
+    if (f->g.mode == 0 && f->w_count <= small_max && m <= 16 * small_max) {
+        // a small field: one launch, one CTA (profile: all of it counted as "scan")
+        if (int rc = mark()) return rc;
+        launch_rebin_small(f->s, f->ncell, (uint32_t)f->w_count, bump_step, f->stream, (uint32_t)f->g.ncols, (uint32_t)f->g.dh);
+        for (int k = 0; k < 3; ++k) if (int rc = mark()) return rc;
+        f->launches += 1;
+    } else {
+        if (int rc = mark()) return rc;
+        launch_scan(f->s, m, f->stream);
+        if (int rc = mark()) return rc;
+        launch_scatter(f->s, (uint32_t)f->w_count, f->g.mode != 0, f->stream);
+        if (int rc = mark()) return rc;
+        launch_rank(f->s, (uint32_t)f->w_count, f->ncell, bump_step, f->stream, (uint32_t)f->g.ncols, (uint32_t)f->g.dh);
+        if (int rc = mark()) return rc;
+        f->launches += 1 + (f->g.mode != 0 ? 2 : (f->w_count ? 1 : 0)) + 1;
+    }
     CUDA_TRY(cudaGetLastError());
     f->n_read = f->w_count;  // single GPU: every WRITE entry is kept
     f->w_count = 0;

@@ -455,7 +455,7 @@ static int dist_publish_uploads(flk_field *f) {
         launch_scatter(f->s, (uint32_t)w, 0, f->stream);
     }
     launch_rank(f->s, (uint32_t)w, f->ncell, 0, f->stream);
-    f->launches += 4 + (w ? 1 : 0);
+    f->launches += 2 + (w ? 1 : 0);
     CUDA_TRY(cudaGetLastError());
     f->n_read = w;
     f->w_count = 0;

@@ -2,9 +2,11 @@
 //
 //   k_step      Bird::step for every bird of the READ buffer (flockers/src/model/bird.rs:27-145), fused with
 //               Field2D::set_object_location (cell key + per-cell arrival slot of the successor, bird.rs:142-144)
-//   k_scan_*    exclusive scan of the per-cell counters  -> cell_start            } Field2D::lazy_update
+//   k_scan_onepass  exclusive scan of the per-cell counters -> cell_start          } Field2D::lazy_update
 //   k_scatter   counting-sort scatter of (id, source index) into cell order       } (flockers/src/model/state.rs:54-56)
 //   k_rank      ascending-id rank inside each cell + gather of the records        }
+//   k_rebin_small   the three of them in one CTA (small fields)
+//   k_step_warp a warp per bird (small fields)
 //   k_ingest    bulk Field2D::set_object_location from host arrays (state.rs:49)
 //   k_query_*   Field2D::get_neighbors_within_{relax_,}distance (bird.rs:29-31)
 //
@@ -780,7 +782,7 @@ void launch_compact_owned(const Geom &g, const Store &s, uint32_t n_upper, uint3
 }
 
 // ------------------------------------------------------------------------------------------------
-// exclusive scan of cnt[0..m) -> cell_start[0..m), zeroing cnt (reduce / spine / down-sweep)
+// exclusive scan of cnt[0..m) -> cell_start[0..m), zeroing cnt
 // ------------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -818,51 +820,66 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
     return r;
 }
 
-// cnt / cell_start are allocated padded to a multiple of SCAN_TILE (zero-filled), so whole-tile uint4 accesses are safe
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t *__restrict__ cnt, uint32_t m,
-                                                              uint32_t *__restrict__ blocksum) {
-    const uint4 *p = reinterpret_cast<const uint4 *>(cnt + (size_t)blockIdx.x * SCAN_TILE) + threadIdx.x * 2;
-    const uint4 a = p[0], b = p[1];
-    const uint32_t v = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
-    uint32_t total;
-    block_exclusive_scan<SCAN_THREADS>(v, &total);
-    if (threadIdx.x == 0) blocksum[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(1024) k_scan_spine(uint32_t *__restrict__ blocksum, uint32_t nblk) {
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < nblk; base += 1024) {
-        const uint32_t idx = base + threadIdx.x;
-        const uint32_t v = idx < nblk ? blocksum[idx] : 0;
-        uint32_t total;
-        const uint32_t ex = block_exclusive_scan<1024>(v, &total);
-        if (idx < nblk) blocksum[idx] = ex + carry;
-        carry += total;
-    }
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_down(uint32_t *__restrict__ cnt, uint32_t m,
-                                                            const uint32_t *__restrict__ blocksum,
-                                                            uint32_t *__restrict__ cell_start) {
-    uint4 *pc = reinterpret_cast<uint4 *>(cnt + (size_t)blockIdx.x * SCAN_TILE) + threadIdx.x * 2;
-    uint4 *ps = reinterpret_cast<uint4 *>(cell_start + (size_t)blockIdx.x * SCAN_TILE) + threadIdx.x * 2;
+// One launch (decoupled look-back; cnt / cell_start are allocated padded to a multiple of SCAN_TILE, zero-filled, so
+// whole-tile uint4 accesses are safe): a CTA takes the next tile by ticket, publishes its tile's total,
+// sums the totals / prefixes its predecessors have published (they took their tickets earlier, so they are running) and
+// publishes its own inclusive prefix.  state[0] = ticket, state[1] = CTAs done, state[2 + t] = {status : value} of tile t
+// (status 0 = nothing yet, 1 = tile total, 2 = inclusive prefix); the last CTA to finish clears the state for the next
+// launch.  Two launches fewer per tick than reduce / spine / down-sweep (round 1): 2 us of a 40-48 us tick at 60-250 k
+// birds, neutral at 16 M.
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(uint32_t *__restrict__ cnt, uint32_t *__restrict__ cell_start,
+                                                               unsigned long long *state, uint32_t nblk) {
+    __shared__ uint32_t sh_tile, sh_excl, sh_last;
+    if (threadIdx.x == 0) sh_tile = (uint32_t)atomicAdd(state, 1ull);
+    __syncthreads();
+    const uint32_t tile = sh_tile;
+    volatile unsigned long long *stt = state + 2;
+    uint4 *pc = reinterpret_cast<uint4 *>(cnt + (size_t)tile * SCAN_TILE) + threadIdx.x * 2;
+    uint4 *ps = reinterpret_cast<uint4 *>(cell_start + (size_t)tile * SCAN_TILE) + threadIdx.x * 2;
     const uint4 a = pc[0], b = pc[1];
     const uint32_t v = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
     uint32_t total;
-    const uint32_t run = block_exclusive_scan<SCAN_THREADS>(v, &total) + blocksum[blockIdx.x];
+    uint32_t run = block_exclusive_scan<SCAN_THREADS>(v, &total);
+    if (threadIdx.x == 0) {
+        stt[tile] = ((tile == 0 ? 2ull : 1ull) << 32) | total;
+        if (tile == 0) sh_excl = 0;
+    }
+    if (tile > 0 && threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        uint32_t excl = 0;
+        for (int idx = (int)tile - 1;; idx -= 32) {
+            const int j = idx - lane;
+            unsigned long long w = 2ull << 32;          // before tile 0: an inclusive prefix of zero
+            if (j >= 0) do { w = stt[j]; } while ((w >> 32) == 0);
+            const unsigned pm = __ballot_sync(0xffffffffu, (w >> 32) == 2);
+            const int first = pm ? __ffs(pm) - 1 : 31;  // the nearest predecessor that already knows its prefix
+            uint32_t val = lane <= first ? (uint32_t)w : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            excl += val;
+            if (pm) break;
+        }
+        if (lane == 0) {
+            stt[tile] = (2ull << 32) | (excl + total);
+            sh_excl = excl;
+        }
+    }
+    __syncthreads();
+    run += sh_excl;
     uint4 o0, o1;
     o0.x = run; o0.y = o0.x + a.x; o0.z = o0.y + a.y; o0.w = o0.z + a.z;
     o1.x = o0.w + a.w; o1.y = o1.x + b.x; o1.z = o1.y + b.y; o1.w = o1.z + b.z;
     ps[0] = o0; ps[1] = o1;
-    // the new WRITE buffer starts empty (lazy_update clears the bags)
-    pc[0] = make_uint4(0, 0, 0, 0); pc[1] = make_uint4(0, 0, 0, 0);
+    pc[0] = make_uint4(0, 0, 0, 0); pc[1] = make_uint4(0, 0, 0, 0);   // the new WRITE buffer starts empty
+    if (threadIdx.x == 0) sh_last = atomicAdd(state + 1, 1ull) == (unsigned long long)nblk - 1;
+    __syncthreads();
+    if (sh_last)   // every CTA is past its look-back
+        for (uint32_t i = threadIdx.x; i < nblk + 2; i += SCAN_THREADS) state[i] = 0;
 }
 
 void launch_scan(const Store &s, uint32_t m, cudaStream_t st) {
     const uint32_t nblk = (m + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_reduce<<<nblk, SCAN_THREADS, 0, st>>>(s.cnt, m, s.blocksum);
-    k_scan_spine<<<1, 1024, 0, st>>>(s.blocksum, nblk);
-    k_scan_down<<<nblk, SCAN_THREADS, 0, st>>>(s.cnt, m, s.blocksum, s.cell_start);
+    k_scan_onepass<<<nblk, SCAN_THREADS, 0, st>>>(s.cnt, s.cell_start, s.scan_state, nblk);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -953,6 +970,7 @@ void launch_scatter(const Store &s, uint32_t n, int dist, cudaStream_t st) {
 }
 
 // colchunk[c] = k_step CTAs needed by the columns before c (column-aligned launches); one CTA, after cell_start is final
+template <int THREADS = 256>
 __device__ __forceinline__ void build_colchunk(const Store &s, uint32_t ncols, uint32_t dh) {
     __shared__ uint32_t sh_carry;
     if (threadIdx.x == 0) sh_carry = 0;
@@ -962,7 +980,7 @@ __device__ __forceinline__ void build_colchunk(const Store &s, uint32_t ncols, u
         uint32_t ch = 0;
         if (c < ncols) ch = (s.cell_start[(c + 1) * dh] - s.cell_start[c * dh] + FLK_STEP_BS - 1) / FLK_STEP_BS;
         uint32_t total;
-        const uint32_t ex = block_exclusive_scan<256>(ch, &total);
+        const uint32_t ex = block_exclusive_scan<THREADS>(ch, &total);
         if (c < ncols) s.colchunk[c] = sh_carry + ex;
         __syncthreads();
         if (threadIdx.x == 0) sh_carry += total;
@@ -1023,6 +1041,66 @@ void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step
     const uint32_t nb = n_upper == 0 ? 1 : ((n_upper + 1) / 2 + 255) / 256;
     if (!s.colchunk) ncols = 0;
     k_rank<<<nb + (ncols ? 1 : 0), 256, 0, st>>>(s, ncell, bump_step, ncols, dh);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_rebin_small: the whole rebin (scan, scatter, rank, colchunk) of a small single-GPU field in ONE CTA — the shipped
+// 1000-bird run (flockers/src/main.rs:40-44) spends its tick in launch latencies, not in work: one launch instead of five.
+// Same arithmetic and the same (cell, ascending id) result as k_scan_onepass + k_scatter4 + k_rank.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_rebin_small(const Store s, uint32_t ncell, uint32_t n_write, int bump_step,
+                                                      uint32_t ncols, uint32_t dh) {
+    const uint32_t m = ncell + 1;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < m; base += 1024) {
+        const uint32_t idx = base + threadIdx.x;
+        const uint32_t v = idx < m ? s.cnt[idx] : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan<1024>(v, &total);
+        if (idx < m) {
+            s.cell_start[idx] = ex + carry;
+            s.cnt[idx] = 0;                    // the new WRITE buffer starts empty
+        }
+        carry += total;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_write; i += 1024) {
+        const uint32_t key = s.tkey[i];
+        if (key == KEY_INVALID) continue;
+        const uint32_t p = s.cell_start[key] + s.tslot[i];
+        if (p >= s.cap) {
+            atomicOr(s.err_flag, ERR_CAPACITY);
+            continue;
+        }
+        s.stage[p] = make_uint4(s.tid[i], i, key, 0u);
+    }
+    __syncthreads();
+    const uint32_t n = min(carry, s.cap);
+    if (threadIdx.x == 0) {
+        *s.n_read_dev = n;
+        if (bump_step) *s.step_dev += 1;
+    }
+    for (uint32_t p0 = threadIdx.x; p0 < n; p0 += 1024) {
+        const uint4 m0 = s.stage[p0];
+        const float4 r0 = reinterpret_cast<const float4 *>(s.trec)[m0.y];
+        const uint32_t lo = s.cell_start[m0.z], hi = min(s.cell_start[m0.z + 1], s.cap);
+        uint32_t k0 = 0;
+        for (uint32_t q = lo; q < hi; ++q) {
+            const uint32_t other = s.stage[q].x;
+            k0 += (other < m0.x) || (other == m0.x && q < p0);
+        }
+        const uint32_t d0 = lo + k0;
+        reinterpret_cast<float4 *>(s.rec)[d0] = r0;
+        s.ids[d0] = m0.x;
+        for (uint32_t k = 0; k < s.pw; ++k) s.pay[(size_t)d0 * s.pw + k] = s.tpay[(size_t)m0.y * s.pw + k];
+    }
+    if (ncols) build_colchunk<1024>(s, ncols, dh);
+}
+
+void launch_rebin_small(const Store &s, uint32_t ncell, uint32_t n_write, int bump_step, cudaStream_t st, uint32_t ncols,
+                        uint32_t dh) {
+    if (!s.colchunk) ncols = 0;
+    k_rebin_small<<<1, 1024, 0, st>>>(s, ncell, n_write, bump_step, ncols, dh);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ struct Store {
     uint32_t *tslot;       // WRITE arrival slot inside its cell
     uint32_t *cnt;         // WRITE per-cell counters (ncell+1)
     uint4 *stage;          // staging for the (cell,id) ranking: {id, WRITE index, cell key, -} in cell order
-    uint32_t *blocksum;    // scan scratch
+    unsigned long long *scan_state;   // one-pass scan: ticket, done counter, one status word per tile (kept zeroed between launches)
     uint64_t *step_dev;    // tick counter used by graph replays
     uint32_t *n_read_dev;  // number of READ objects (device copy)
     uint32_t *err_flag;    // device-side error bits (ERR_*)
@@ -108,6 +108,10 @@ void launch_scan(const Store &s, uint32_t ncell_plus1, cudaStream_t st);
 void launch_scatter(const Store &s, uint32_t n_write_extent, int dist, cudaStream_t st);
 void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step, cudaStream_t st, uint32_t ncols = 0, uint32_t dh = 0);
 // slot-staged WRITE buffer -> READ buffer in (cell, ascending id) order, given cell_start (one pass, 8 lanes per cell)
+// the whole rebin of a small single-GPU field (classic WRITE buffer) in one launch
+constexpr uint32_t SMALL_REBIN_MAX = 4096;   // birds: up to here one CTA beats the five-launch rebin
+void launch_rebin_small(const Store &s, uint32_t ncell, uint32_t n_write, int bump_step, cudaStream_t st, uint32_t ncols,
+                        uint32_t dh);
 void launch_compact(const Store &s, uint32_t ncell, int bump_step, cudaStream_t st, uint32_t ncols = 0, uint32_t dh = 0);
 void launch_selftest_div2(uint64_t n, uint64_t seed, unsigned long long *mismatches, cudaStream_t st);
 void launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t st);
