@@ -424,7 +424,7 @@ int enqueue_lazy_update(flk_field *f, int bump_step) {
         if (int rc = mark()) return rc;
         launch_rank(f->s, (uint32_t)f->w_count, f->ncell, bump_step, f->stream, (uint32_t)f->g.ncols, (uint32_t)f->g.dh);
         if (int rc = mark()) return rc;
-        f->launches += 1 + (f->g.mode != 0 ? 2 : (f->w_count ? 1 : 0)) + 1;
+        f->launches += 1 + ((f->g.mode != 0 || f->w_count) ? 1 : 0) + 1;
     }
     CUDA_TRY(cudaGetLastError());
     f->n_read = f->w_count;  // single GPU: every WRITE entry is kept

@@ -885,23 +885,14 @@ void launch_scan(const Store &s, uint32_t m, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // k_scatter / k_rank: WRITE buffer -> READ buffer in (cell, ascending id) order
 // ------------------------------------------------------------------------------------------------
-template <bool DIST>
-__global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n, uint32_t base) {
-    const uint32_t i = base + blockIdx.x * blockDim.x + threadIdx.x;
-    if (DIST) {
-        // valid WRITE slots: [0, n_read) stepped, [cap, cap+countL) and [cap+capx, cap+capx+countR) received
-        if (i < s.cap) {
-            if (i >= *s.n_read_dev) return;
-        } else {
-            const uint32_t t = i - s.cap;
-            if (t >= s.nrecv * s.capx) return;
-            const uint32_t b = t / s.capx;
-            const uint8_t *buf = b == 0 ? s.recvL : (b == 1 ? s.recvR : (b == 2 ? s.recvD : s.recvU));
-            if (t - b * s.capx >= min(reinterpret_cast<const XHdr *>(buf)->count, s.capx)) return;
-        }
-    } else if (i >= n) {
-        return;
-    }
+// strips / tiles: the arrivals unpacked into the receive regions of the WRITE buffer, [cap + b*capx, cap + b*capx +
+// count_b) for message b; one slot per thread, t = index into the receive regions
+__device__ __forceinline__ void scatter_received(const Store &s, uint32_t t) {
+    if (t >= s.nrecv * s.capx) return;
+    const uint32_t b = t / s.capx;
+    const uint8_t *buf = b == 0 ? s.recvL : (b == 1 ? s.recvR : (b == 2 ? s.recvD : s.recvU));
+    if (t - b * s.capx >= min(reinterpret_cast<const XHdr *>(buf)->count, s.capx)) return;
+    const uint32_t i = s.cap + t;
     const uint32_t key = s.tkey[i];
     if (key == KEY_INVALID) return;
     const uint32_t p = s.cell_start[key] + s.tslot[i];
@@ -917,8 +908,12 @@ __global__ void __launch_bounds__(256) k_scatter(const Store s, uint32_t n, uint
 #ifndef FLK_SCATTER_E
 #define FLK_SCATTER_E 4   // WRITE slots per thread (multiple of 4)
 #endif
-__global__ void __launch_bounds__(256) k_scatter4(const Store s, uint32_t n_limit, int use_dev_count) {
+__global__ void __launch_bounds__(256) k_scatter4(const Store s, uint32_t n_limit, int use_dev_count, uint32_t nb_stepped) {
     constexpr int E = FLK_SCATTER_E;
+    if (blockIdx.x >= nb_stepped) {   // strips / tiles: the CTAs behind the stepped slots take the receive regions
+        scatter_received(s, (blockIdx.x - nb_stepped) * blockDim.x + threadIdx.x);
+        return;
+    }
     const uint32_t n = use_dev_count ? min(*s.n_read_dev, n_limit) : n_limit;
     const uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) * (uint32_t)E;
     if (i0 >= n) return;
@@ -961,12 +956,13 @@ void launch_scatter(const Store &s, uint32_t n, int dist, cudaStream_t st) {
     if (dist) {
         // stepped slots [0, n) (n = host upper bound of the READ population), then the two receive regions
         const uint32_t nn = n < s.cap ? n : s.cap;
-        if (nn) k_scatter4<<<((nn + FLK_SCATTER_E - 1) / FLK_SCATTER_E + 255) / 256, 256, 0, st>>>(s, nn, 1);
-        k_scatter<true><<<(s.nrecv * s.capx + 255) / 256, 256, 0, st>>>(s, s.nrecv * s.capx, s.cap);
+        const uint32_t nb = ((nn + FLK_SCATTER_E - 1) / FLK_SCATTER_E + 255) / 256;
+        k_scatter4<<<nb + (s.nrecv * s.capx + 255) / 256, 256, 0, st>>>(s, nn, 1, nb);
         return;
     }
     if (n == 0) return;
-    k_scatter4<<<((n + FLK_SCATTER_E - 1) / FLK_SCATTER_E + 255) / 256, 256, 0, st>>>(s, n, 0);
+    const uint32_t nb = ((n + FLK_SCATTER_E - 1) / FLK_SCATTER_E + 255) / 256;
+    k_scatter4<<<nb, 256, 0, st>>>(s, n, 0, nb);
 }
 
 // colchunk[c] = k_step CTAs needed by the columns before c (column-aligned launches); one CTA, after cell_start is final
