@@ -36,7 +36,7 @@ int field_alloc(flk_field *f) {
     const uint64_t capw = cap + (uint64_t)s.nrecv * s.capx;   // WRITE slots: stepped/uploaded + received from the neighbours
     CUDA_TRY(cudaMalloc(&s.rec, cap * sizeof(Rec)));
     CUDA_TRY(cudaMalloc(&s.ids, cap * 4));
-    const uint64_t mp = ((m + 2047) / 2048) * 2048;   // padded to the scan tile (k_scan_onepass uses whole-tile vector accesses)
+    const uint64_t mp = ((m + 4095) / 4096) * 4096;   // padded to the widest scan tile (k_scan_onepass uses whole-tile vector accesses)
     CUDA_TRY(cudaMalloc(&s.cell_start, mp * 4));
     CUDA_TRY(cudaMalloc(&s.trec, capw * sizeof(Rec)));
     CUDA_TRY(cudaMalloc(&s.tid, capw * 4));

@@ -787,6 +787,7 @@ void launch_compact_owned(const Geom &g, const Store &s, uint32_t n_upper, uint3
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr uint32_t SCAN_WIDE_MIN = 1u << 21;   // cells: above, 16 counters per thread (cnt / cell_start are padded to 2 * SCAN_TILE)
 
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v) {
     const int lane = threadIdx.x & 31;
@@ -827,17 +828,24 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
 // (status 0 = nothing yet, 1 = tile total, 2 = inclusive prefix); the last CTA to finish clears the state for the next
 // launch.  Two launches fewer per tick than reduce / spine / down-sweep (round 1): 2 us of a 40-48 us tick at 60-250 k
 // birds, neutral at 16 M.
+template <int ITEMS>   // counters per thread: 8 (tiles of 2048 cells) or 16 (4096: half as many look-backs for large fields)
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(uint32_t *__restrict__ cnt, uint32_t *__restrict__ cell_start,
                                                                unsigned long long *state, uint32_t nblk) {
+    constexpr int Q = ITEMS / 4;
     __shared__ uint32_t sh_tile, sh_excl, sh_last;
     if (threadIdx.x == 0) sh_tile = (uint32_t)atomicAdd(state, 1ull);
     __syncthreads();
     const uint32_t tile = sh_tile;
     volatile unsigned long long *stt = state + 2;
-    uint4 *pc = reinterpret_cast<uint4 *>(cnt + (size_t)tile * SCAN_TILE) + threadIdx.x * 2;
-    uint4 *ps = reinterpret_cast<uint4 *>(cell_start + (size_t)tile * SCAN_TILE) + threadIdx.x * 2;
-    const uint4 a = pc[0], b = pc[1];
-    const uint32_t v = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    uint4 *pc = reinterpret_cast<uint4 *>(cnt + (size_t)tile * (SCAN_THREADS * ITEMS)) + threadIdx.x * Q;
+    uint4 *ps = reinterpret_cast<uint4 *>(cell_start + (size_t)tile * (SCAN_THREADS * ITEMS)) + threadIdx.x * Q;
+    uint4 c[Q];
+    uint32_t v = 0;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        c[q] = pc[q];
+        v += c[q].x + c[q].y + c[q].z + c[q].w;
+    }
     uint32_t total;
     uint32_t run = block_exclusive_scan<SCAN_THREADS>(v, &total);
     if (threadIdx.x == 0) {
@@ -866,11 +874,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(uint32_t *__restr
     }
     __syncthreads();
     run += sh_excl;
-    uint4 o0, o1;
-    o0.x = run; o0.y = o0.x + a.x; o0.z = o0.y + a.y; o0.w = o0.z + a.z;
-    o1.x = o0.w + a.w; o1.y = o1.x + b.x; o1.z = o1.y + b.y; o1.w = o1.z + b.z;
-    ps[0] = o0; ps[1] = o1;
-    pc[0] = make_uint4(0, 0, 0, 0); pc[1] = make_uint4(0, 0, 0, 0);   // the new WRITE buffer starts empty
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        uint4 o;
+        o.x = run; o.y = o.x + c[q].x; o.z = o.y + c[q].y; o.w = o.z + c[q].z;
+        run = o.w + c[q].w;
+        ps[q] = o;
+        pc[q] = make_uint4(0, 0, 0, 0);   // the new WRITE buffer starts empty
+    }
     if (threadIdx.x == 0) sh_last = atomicAdd(state + 1, 1ull) == (unsigned long long)nblk - 1;
     __syncthreads();
     if (sh_last)   // every CTA is past its look-back
@@ -878,8 +889,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(uint32_t *__restr
 }
 
 void launch_scan(const Store &s, uint32_t m, cudaStream_t st) {
-    const uint32_t nblk = (m + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_onepass<<<nblk, SCAN_THREADS, 0, st>>>(s.cnt, s.cell_start, s.scan_state, nblk);
+    if (m > SCAN_WIDE_MIN) {
+        const uint32_t nblk = (m + 2 * SCAN_TILE - 1) / (2 * SCAN_TILE);
+        k_scan_onepass<2 * SCAN_ITEMS><<<nblk, SCAN_THREADS, 0, st>>>(s.cnt, s.cell_start, s.scan_state, nblk);
+    } else {
+        const uint32_t nblk = (m + SCAN_TILE - 1) / SCAN_TILE;
+        k_scan_onepass<SCAN_ITEMS><<<nblk, SCAN_THREADS, 0, st>>>(s.cnt, s.cell_start, s.scan_state, nblk);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
