@@ -882,7 +882,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_onepass(uint32_t *__restr
         ps[q] = o;
         pc[q] = make_uint4(0, 0, 0, 0);   // the new WRITE buffer starts empty
     }
-    if (threadIdx.x == 0) sh_last = atomicAdd(state + 1, 1ull) == (unsigned long long)nblk - 1;
+    if (threadIdx.x == 0) {
+        // release: this thread's status stores must have landed before the CTA counts as done — the last CTA clears the
+        // state words, and a status store arriving after that would survive into the next launch (seen as a stale
+        // inclusive prefix there: with four strips sharing one GPU this happened once in a few hundred ticks)
+        __threadfence();
+        sh_last = atomicAdd(state + 1, 1ull) == (unsigned long long)nblk - 1;
+    }
     __syncthreads();
     if (sh_last)   // every CTA is past its look-back
         for (uint32_t i = threadIdx.x; i < nblk + 2; i += SCAN_THREADS) state[i] = 0;
