@@ -532,7 +532,7 @@ def run_ours(args, world: int, rank: int, local_rank: int):
     # ---- the other BASELINE configs, short legs (driver-visible numbers for configs 2, 3 and 5) ----
     extras = {}
     if not args.no_extras and args.workload == "weak16m" and args.birds_per_gpu is None:
-        legs = [("shipped", 2000), ("1m", 200), ("clustered", 10)] if world == 1 else [("strong16m", 100)]
+        legs = [("shipped", 2000), ("1m", 200), ("clustered", 10)] if world == 1 else [("strong16m", 100), ("clustered", 10)]
         for name, k in legs:
             try:
                 w2 = build_field(name, None)
