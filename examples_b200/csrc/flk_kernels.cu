@@ -821,8 +821,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
     return r;
 }
 
-// One launch (decoupled look-back; cnt / cell_start are allocated padded to a multiple of SCAN_TILE, zero-filled, so
-// whole-tile uint4 accesses are safe): a CTA takes the next tile by ticket, publishes its tile's total,
+// One launch (decoupled look-back; cnt / cell_start are allocated padded to a multiple of the widest tile, 2 * SCAN_TILE,
+// zero-filled, so whole-tile uint4 accesses are safe): a CTA takes the next tile by ticket, publishes its tile's total,
 // sums the totals / prefixes its predecessors have published (they took their tickets earlier, so they are running) and
 // publishes its own inclusive prefix.  state[0] = ticket, state[1] = CTAs done, state[2 + t] = {status : value} of tile t
 // (status 0 = nothing yet, 1 = tile total, 2 = inclusive prefix); the last CTA to finish clears the state for the next
