@@ -50,8 +50,8 @@ int field_alloc(flk_field *f) {
     CUDA_TRY(cudaMalloc(&s.scan_state, (nblk + 2) * 8));
     CUDA_TRY(cudaMemsetAsync(s.scan_state, 0, (nblk + 2) * 8, f->stream));
     if (f->g.mode == 0) {   // column-aligned k_step launches (single-GPU handles)
-        CUDA_TRY(cudaMalloc(&s.colchunk, ((uint64_t)f->g.ncols + 1) * 4));
-        CUDA_TRY(cudaMemsetAsync(s.colchunk, 0, ((uint64_t)f->g.ncols + 1) * 4, f->stream));
+        CUDA_TRY(cudaMalloc(&s.colchunk, 2 * ((uint64_t)f->g.ncols + 1) * 4));   // chunk table + seam-bird table
+        CUDA_TRY(cudaMemsetAsync(s.colchunk, 0, 2 * ((uint64_t)f->g.ncols + 1) * 4, f->stream));
     }
     CUDA_TRY(cudaMalloc(&s.step_dev, 8));
     CUDA_TRY(cudaMalloc(&s.n_read_dev, 4));
@@ -448,7 +448,7 @@ int enqueue_step(flk_field *f, uint64_t step, int use_step_dev, uint64_t seed, c
     a.math_mode = f->math_mode;
     a.identity = 0;
     a.skip_bands = 0;
-    a.nseam = 0;
+    a.nseam = 0; a.gen_threads = 0;
     const bool prof = f->profile && !f->capturing;
     if (prof) {
         cudaEvent_t e0, e1;

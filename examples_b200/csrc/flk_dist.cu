@@ -283,7 +283,7 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
     a.math_mode = f->math_mode;
     a.identity = identity;
     a.skip_bands = 0;
-    a.nseam = 0;
+    a.nseam = 0; a.gen_threads = 0;
     const bool prof = f->profile && !identity;
     if (prof) {
         cudaEvent_t e0, e1;
@@ -321,7 +321,7 @@ static int dist_phase_step(flk_field *f, uint64_t step, uint64_t seed, const flo
         a.skip_bands = d->bands ? 1 : 0;
         launch_step(f->g, f->p, f->s, a, read_upper_bound(f), f->stream);
         a.skip_bands = 0;
-    a.nseam = 0;
+    a.nseam = 0; a.gen_threads = 0;
         f->launches += 1;
     } else {
         d->bands = false;

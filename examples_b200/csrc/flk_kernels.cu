@@ -282,6 +282,137 @@ __device__ __noinline__ void step_bird_general(const Geom &g, const Params &p, c
     finish_bird<MATH, false, TILES ? 1 : 0>(g, p, s, a, me, my_id, w, acc, d_ok, Rd, i);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_step_warp: Bird::step with ONE WARP PER BIRD, for fields too small to fill the GPU with a thread per bird (the
+// shipped run: 1000 birds = 8 CTAs of k_step, one warp per scheduler, ~8 000 dependent instructions each: 32 us).
+// The lanes share the bird's candidates: every window run is taken 32 candidates at a time, each lane computes the pair
+// terms of one candidate (bird.rs:54-61: toroidal distances, square, the two exact quotients) and parks them in shared
+// memory; then six lanes — one per accumulator of bird.rs:44-49 — add the parked terms in candidate order, so every f32
+// sum is evaluated in exactly the order of the thread-per-bird kernels.  Lane 0 finishes the bird.  Any window width,
+// either query, seam or not, strips too (rows not split).
+// ------------------------------------------------------------------------------------------------
+constexpr int WARP_RUNS = 32;   // window runs a warp keeps in shared memory (3 or 9 for the shipped 3x3 window; 49 for 7x7 -> general kernel)
+
+// Bird::step of READ bird i by the 32 lanes of the calling warp (all of them); term / run_start / run_pre: the warp's own
+// shared-memory scratch (6 x 32 floats, 2 x (WARP_RUNS + 1) words)
+template <bool RELAX, int MATH>
+__device__ __forceinline__ void step_bird_warp(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t i,
+                                               float (*term)[32], uint32_t *run_start, uint32_t *run_pre) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = a.out_base + i;
+    const Rec me = s.rec[i];
+    const uint32_t my_id = s.ids[i];
+    const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
+    const Recip Rd = make_recip(g.d);
+    const int gcx = cell_coord(me.x, g.d, g.mx + 1);
+    const int cy = cell_coord(me.y, g.d, g.dh);
+    const int lc = local_col(g, gcx);
+    if (g.mode != 0 && (lc == 0 || lc == g.nown + 1)) {    // ghost copy: stepped by its owner, dropped here
+        if (lane == 0 && !s.slotw) s.tkey[w] = KEY_INVALID;
+        return;
+    }
+    if (a.identity) {                                      // dist commit: re-stage the bird unchanged
+        if (lane == 0) emit_successor<false, 0>(g, s, me, my_id, w, d_ok, Rd, i);
+        return;
+    }
+    const float W = g.W, H = g.H;
+    const float halfW = __fdiv_rn(W, 2.0f), halfH = __fdiv_rn(H, 2.0f);
+    float acc_l = 0.0f;                                    // lanes 0..5: x_avoid, y_avoid, x_cohe, y_cohe, x_cons, y_cons
+    uint32_t nvec = 0;
+    int count = 0;
+    const float4 *__restrict__ rec = reinterpret_cast<const float4 *>(s.rec);
+    if (p.radius > 0.0f) {                                 // both queries return nothing for dist <= 0
+        // ---- the window's runs in query order (all their bounds are requested before any is used)
+        int nruns = 0;
+        uint32_t total = 0;
+        for_each_window_run<0>(g, s.cell_start, lc, cy, p.k, [&](uint32_t rs, uint32_t re) {
+            if (lane == 0 && nruns < WARP_RUNS) { run_start[nruns] = rs; run_pre[nruns] = total; }
+            total += re - rs;
+            ++nruns;
+        });
+        if (lane == 0 && nruns <= WARP_RUNS) run_pre[nruns] = total;
+        __syncwarp();
+        // ---- candidates 32 at a time, by their position in the query result
+        for (uint32_t c0 = 0; c0 < total; c0 += 32) {
+            const uint32_t c = c0 + (uint32_t)lane;
+            bool keep = c < total;
+            bool self = false;
+            if (keep) {
+                int r = 0;
+                for (int q = 1; q < nruns; ++q) r += run_pre[q] <= c ? 1 : 0;     // the run that holds candidate c
+                const uint32_t j = run_start[r] + (c - run_pre[r]);
+                self = j == i;                                                     // bird.rs:53
+                const float4 o = __ldg(rec + j);
+                const float dx = toroidal_distance(me.x, o.x, W, halfW);           // bird.rs:54
+                const float dy = toroidal_distance(me.y, o.y, H, halfH);           // bird.rs:55
+                const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));  // :59
+                if (!RELAX) {   // get_neighbors_within_distance keeps elem iff sqrt(dx^2+dy^2) <= dist (SURVEY E7)
+                    float qs = sq;
+                    if (!g.toroidal) {
+                        const float px = __fadd_rn(me.x, -o.x), py = __fadd_rn(me.y, -o.y);
+                        qs = __fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py));
+                    }
+                    keep = __fsqrt_rn(qs) <= p.radius;
+                }
+                const float den = __fadd_rn(__fmul_rn(sq, sq), 1.0f);
+                float qa, qb;
+                if (MATH == 0) {
+                    div2_rn(dx, dy, den, qa, qb);          // :60-61, two IEEE divisions
+                } else {
+                    float inv;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
+                    qa = __fmul_rn(dx, inv);
+                    qb = __fmul_rn(dy, inv);
+                }
+                term[0][lane] = qa; term[1][lane] = qb;       // :60-61
+                term[2][lane] = dx; term[3][lane] = dy;       // :64-65
+                term[4][lane] = o.z; term[5][lane] = o.w;     // :68-69
+            }
+            const uint32_t kept = __ballot_sync(0xffffffffu, keep);
+            const uint32_t add = kept & ~__ballot_sync(0xffffffffu, self);
+            nvec += (uint32_t)__popc(kept);
+            count += __popc(add);                          // :56
+            __syncwarp();
+            if (lane < 6) {
+                uint32_t m = add;
+                while (m) {                                // candidates in order, one rounded addition each
+                    const int e = __ffs(m) - 1;
+                    m &= m - 1;
+                    acc_l = __fadd_rn(acc_l, term[lane][e]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    Acc acc;
+    acc.xa = __shfl_sync(0xffffffffu, acc_l, 0); acc.ya = __shfl_sync(0xffffffffu, acc_l, 1);
+    acc.xc = __shfl_sync(0xffffffffu, acc_l, 2); acc.yc = __shfl_sync(0xffffffffu, acc_l, 3);
+    acc.xs = __shfl_sync(0xffffffffu, acc_l, 4); acc.ys = __shfl_sync(0xffffffffu, acc_l, 5);
+    acc.nvec = nvec; acc.count = count;
+    if (lane == 0) finish_bird<MATH, false, 0>(g, p, s, a, me, my_id, w, acc, d_ok, Rd, i);
+}
+
+template <bool RELAX, int MATH>
+__global__ void __launch_bounds__(128) k_step_warp(const __grid_constant__ Geom g, const __grid_constant__ Params p,
+                                                   const __grid_constant__ Store s, const __grid_constant__ StepArgs a) {
+    __shared__ float term_s[4][6][32];
+    __shared__ uint32_t run_s[4][2][WARP_RUNS + 1];        // [0]: first READ index of each run, [1]: candidates before it
+    const int wid = threadIdx.x >> 5;
+    const uint32_t lo = a.cell_lo ? __ldg(s.cell_start + a.cell_lo) : 0u;
+    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && hi - lo > gridDim.x * 4u) atomicOr(s.err_flag, ERR_EXCHANGE);
+    const uint32_t i = lo + blockIdx.x * 4u + (uint32_t)wid;
+    if (i >= hi) return;                                   // warp-uniform
+    step_bird_warp<RELAX, MATH>(g, p, s, a, i, term_s[wid], run_s[wid][0], run_s[wid][1]);
+}
+
+// out of line for k_step's column-aligned launches (own register allocation, like step_bird_general)
+template <bool RELAX, int MATH>
+__device__ __noinline__ void step_bird_warp_ool(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t i,
+                                                float (*term)[32], uint32_t *run_start, uint32_t *run_pre) {
+    step_bird_warp<RELAX, MATH>(g, p, s, a, i, term, run_start, run_pre);
+}
+
 // k_step: one thread per READ bird.  TILE = stage the CTA's three window-column runs in shared memory with TMA bulk
 // copies when the CTA's birds sit in one interior column (the common case); other CTAs take step_bird_general.
 // FASTG = the host checked what does not depend on the bird (launch_step): toroidal field, 3x3 window, relax query,
@@ -293,9 +424,10 @@ __device__ __noinline__ void step_bird_general(const Geom &g, const Params &p, c
 // COLS (single-GPU handles, with TILE and FASTG): the grid is aligned to the cell columns.  After the a.nseam seam CTAs, CTA
 // b steps one chunk of FLK_STEP_BS birds of ONE column (s.colchunk maps chunks to columns), so no CTA straddles two
 // columns, and a CTA that starts or ends a column stages the rows it has (clamped at the seam) instead of leaving the tile
-// path: the birds of the seam rows 0, my-1 and my (slack) of such a column need the full toroidal distance and are stepped
-// by the seam CTAs at the head of the grid, one warp per seam cell.  The chunks of the last two columns (x seam and slack:
-// general path, several times slower per CTA) are taken first as well, so that no slow CTA starts in the last wave.
+// path.  The birds that need the full toroidal distance — the seam rows 0, my-1 and my (slack) of those columns and all of
+// columns 0, mx-1 and mx (slack) — are stepped by the a.nseam CTAs at the head of the grid: with ONE WARP PER BIRD
+// (step_bird_warp) while they fit about one wave — a thread per bird on the general path takes ~25 us, which in a launch
+// of a few waves is the launch — and with a thread per bird, all lanes busy, in larger fields (a.gen_threads).
 template <bool RELAX, int MATH, bool TILE, bool FASTG, bool TILES = false, bool COLS = false>
 __global__ void __launch_bounds__(FLK_STEP_BS, FLK_STEP_MINBLOCKS)
 k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const __grid_constant__ Store s,
@@ -304,28 +436,52 @@ k_step(const __grid_constant__ Geom g, const __grid_constant__ Params p, const _
     float4 *const tile[3] = {tile_s, tile_s + (TILE ? TILE_CAP : 0), tile_s + (TILE ? 2 * TILE_CAP : 0)};
     __shared__ __align__(8) uint64_t bar;
     __shared__ int shc[TILES ? 7 : 5];
+    __shared__ float term_w[COLS ? FLK_STEP_BS / 32 : 1][6][32];                  // COLS: scratch of step_bird_warp
+    __shared__ uint32_t run_w[COLS ? FLK_STEP_BS / 32 : 1][2][WARP_RUNS + 1];
 
     // cell_start[0] is 0 by construction: a whole-field launch knows its first bird without a load, so the bird's own
     // record (read speculatively: any index below cap is allocated) is in flight together with the range end
     uint32_t lo, hi, first;
     if (COLS) {
-        const uint32_t dhc = (uint32_t)g.dh;
+        const uint32_t dhc = (uint32_t)g.dh, ncols = (uint32_t)g.ncols;
         if (blockIdx.x < a.nseam) {
-            // ---- seam rows of the tile columns: one warp per cell (rows 0, my-1, my of columns 1 .. mx-2)
-            const uint32_t wq = blockIdx.x * (FLK_STEP_BS / 32) + (threadIdx.x >> 5);
-            const uint32_t c = 1u + wq / 3u, k3 = wq % 3u;
-            if ((int)c > g.mx - 2) return;
-            const uint32_t row = k3 == 0 ? 0u : (k3 == 1 ? (uint32_t)g.my - 1u : (uint32_t)g.my);
-            const uint32_t b0 = __ldg(s.cell_start + c * dhc + row), b1 = __ldg(s.cell_start + c * dhc + row + 1);
-            for (uint32_t q = b0 + (threadIdx.x & 31u); q < b1; q += 32) step_bird_general<RELAX, MATH, TILES>(g, p, s, a, q, a.out_base + q);
+            // ---- the birds that need the general path, ONE WARP EACH (they are few, and a thread per bird takes ~25 us
+            // for one of them: in a launch of a few waves that would be the launch): column 0, then columns mx-1 and
+            // mx (slack), then the seam rows 0, my-1, my of the tile columns
+            const int wid = threadIdx.x >> 5;
+            const uint32_t *cs = s.cell_start;
+            const uint32_t nA = __ldg(cs + dhc), bB = __ldg(cs + (ncols - 2) * dhc), nB = __ldg(cs + ncols * dhc) - bB;
+            const uint32_t *colseam = s.colchunk + ncols + 1;
+            const uint32_t nS = __ldg(colseam + ncols), ngen = nA + nB + nS;
+            auto general_bird = [&](uint32_t wq) -> uint32_t {   // READ index of general bird number wq
+                if (wq < nA) return wq;
+                if (wq < nA + nB) return bB + (wq - nA);
+                const uint32_t q = wq - nA - nB;
+                uint32_t c = min(ncols - 1, (uint32_t)(((uint64_t)q * ncols) / nS));
+                while (__ldg(colseam + c) > q) --c;
+                while (__ldg(colseam + c + 1) <= q) ++c;
+                const uint32_t r = q - __ldg(colseam + c);
+                const uint32_t c0 = __ldg(cs + c * dhc), n0 = __ldg(cs + c * dhc + 1) - c0;
+                return r < n0 ? c0 + r : __ldg(cs + (c + 1) * dhc - 2) + (r - n0);
+            };
+            if (a.gen_threads) {
+                // a field of many waves: a THREAD per general bird (the warps would need several waves of their own;
+                // here the slow threads start first and finish inside the launch)
+                for (uint32_t tq = blockIdx.x * FLK_STEP_BS + threadIdx.x; tq < ngen; tq += a.nseam * FLK_STEP_BS) {
+                    const uint32_t i = general_bird(tq);
+                    step_bird_general<RELAX, MATH, TILES>(g, p, s, a, i, a.out_base + i);
+                }
+                return;
+            }
+            for (uint32_t wq = blockIdx.x * (FLK_STEP_BS / 32) + (uint32_t)wid; wq < ngen; wq += a.nseam * (FLK_STEP_BS / 32)) {
+                const uint32_t i = general_bird(wq);
+                step_bird_warp_ool<RELAX, MATH>(g, p, s, a, i, term_w[wid], run_w[wid][0], run_w[wid][1]);
+            }
             return;
         }
-        const uint32_t ncols = (uint32_t)g.ncols, nch = __ldg(s.colchunk + ncols);
-        uint32_t B = blockIdx.x - a.nseam;
+        const uint32_t nch = __ldg(s.colchunk + ncols);
+        const uint32_t B = blockIdx.x - a.nseam;
         if (B >= nch) return;
-        // the chunks of the last two columns first (see above), then columns 0 .. mx-2 in order
-        const uint32_t tailc = nch - __ldg(s.colchunk + ncols - 2);
-        B = B < tailc ? nch - tailc + B : B - tailc;
         uint32_t c = min(ncols - 1, (uint32_t)(((uint64_t)B * ncols) / nch));
         while (__ldg(s.colchunk + c) > B) --c;
         while (__ldg(s.colchunk + c + 1) <= B) ++c;
@@ -482,130 +638,21 @@ void launch_step_bands(const Geom &g, const Params &p, const Store &s, const Ste
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_step_warp: Bird::step with ONE WARP PER BIRD, for fields too small to fill the GPU with a thread per bird (the
-// shipped run: 1000 birds = 8 CTAs of k_step, one warp per scheduler, ~8 000 dependent instructions each: 32 us).
-// The lanes share the bird's candidates: every window run is taken 32 candidates at a time, each lane computes the pair
-// terms of one candidate (bird.rs:54-61: toroidal distances, square, the two exact quotients) and parks them in shared
-// memory; then six lanes — one per accumulator of bird.rs:44-49 — add the parked terms in candidate order, so every f32
-// sum is evaluated in exactly the order of the thread-per-bird kernels.  Lane 0 finishes the bird.  Any window width,
-// either query, seam or not, strips too (rows not split).
-// ------------------------------------------------------------------------------------------------
-constexpr int WARP_RUNS = 32;   // window runs a warp keeps in shared memory (3 or 9 for the shipped 3x3 window; 49 for 7x7 -> general kernel)
-
-template <bool RELAX, int MATH>
-__global__ void __launch_bounds__(128) k_step_warp(const __grid_constant__ Geom g, const __grid_constant__ Params p,
-                                                   const __grid_constant__ Store s, const __grid_constant__ StepArgs a) {
-    __shared__ float term_s[4][6][32];
-    __shared__ uint32_t run_s[4][2][WARP_RUNS + 1];        // [0]: first READ index of each run, [1]: candidates before it
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float (*term)[32] = term_s[wid];
-    uint32_t *run_start = run_s[wid][0], *run_pre = run_s[wid][1];
-    const uint32_t lo = a.cell_lo ? __ldg(s.cell_start + a.cell_lo) : 0u;
-    const uint32_t hi = __ldg(s.cell_start + a.cell_hi);
-    if (blockIdx.x == 0 && threadIdx.x == 0 && hi - lo > gridDim.x * 4u) atomicOr(s.err_flag, ERR_EXCHANGE);
-    const uint32_t i = lo + blockIdx.x * 4u + (uint32_t)wid;
-    if (i >= hi) return;                                   // warp-uniform
-    const uint32_t w = a.out_base + i;
-    const Rec me = s.rec[i];
-    const uint32_t my_id = s.ids[i];
-    const bool d_ok = g.d >= 0x1p-20f && g.d <= 4096.0f;
-    const Recip Rd = make_recip(g.d);
-    const int gcx = cell_coord(me.x, g.d, g.mx + 1);
-    const int cy = cell_coord(me.y, g.d, g.dh);
-    const int lc = local_col(g, gcx);
-    if (g.mode != 0 && (lc == 0 || lc == g.nown + 1)) {    // ghost copy: stepped by its owner, dropped here
-        if (lane == 0 && !s.slotw) s.tkey[w] = KEY_INVALID;
-        return;
-    }
-    if (a.identity) {                                      // dist commit: re-stage the bird unchanged
-        if (lane == 0) emit_successor<false, 0>(g, s, me, my_id, w, d_ok, Rd, i);
-        return;
-    }
-    const float W = g.W, H = g.H;
-    const float halfW = __fdiv_rn(W, 2.0f), halfH = __fdiv_rn(H, 2.0f);
-    float acc_l = 0.0f;                                    // lanes 0..5: x_avoid, y_avoid, x_cohe, y_cohe, x_cons, y_cons
-    uint32_t nvec = 0;
-    int count = 0;
-    const float4 *__restrict__ rec = reinterpret_cast<const float4 *>(s.rec);
-    if (p.radius > 0.0f) {                                 // both queries return nothing for dist <= 0
-        // ---- the window's runs in query order (all their bounds are requested before any is used)
-        int nruns = 0;
-        uint32_t total = 0;
-        for_each_window_run<0>(g, s.cell_start, lc, cy, p.k, [&](uint32_t rs, uint32_t re) {
-            if (lane == 0 && nruns < WARP_RUNS) { run_start[nruns] = rs; run_pre[nruns] = total; }
-            total += re - rs;
-            ++nruns;
-        });
-        if (lane == 0 && nruns <= WARP_RUNS) run_pre[nruns] = total;
-        __syncwarp();
-        // ---- candidates 32 at a time, by their position in the query result
-        for (uint32_t c0 = 0; c0 < total; c0 += 32) {
-            const uint32_t c = c0 + (uint32_t)lane;
-            bool keep = c < total;
-            bool self = false;
-            if (keep) {
-                int r = 0;
-                for (int q = 1; q < nruns; ++q) r += run_pre[q] <= c ? 1 : 0;     // the run that holds candidate c
-                const uint32_t j = run_start[r] + (c - run_pre[r]);
-                self = j == i;                                                     // bird.rs:53
-                const float4 o = __ldg(rec + j);
-                const float dx = toroidal_distance(me.x, o.x, W, halfW);           // bird.rs:54
-                const float dy = toroidal_distance(me.y, o.y, H, halfH);           // bird.rs:55
-                const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));  // :59
-                if (!RELAX) {   // get_neighbors_within_distance keeps elem iff sqrt(dx^2+dy^2) <= dist (SURVEY E7)
-                    float qs = sq;
-                    if (!g.toroidal) {
-                        const float px = __fadd_rn(me.x, -o.x), py = __fadd_rn(me.y, -o.y);
-                        qs = __fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py));
-                    }
-                    keep = __fsqrt_rn(qs) <= p.radius;
-                }
-                const float den = __fadd_rn(__fmul_rn(sq, sq), 1.0f);
-                float qa, qb;
-                if (MATH == 0) {
-                    div2_rn(dx, dy, den, qa, qb);          // :60-61, two IEEE divisions
-                } else {
-                    float inv;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(den));
-                    qa = __fmul_rn(dx, inv);
-                    qb = __fmul_rn(dy, inv);
-                }
-                term[0][lane] = qa; term[1][lane] = qb;       // :60-61
-                term[2][lane] = dx; term[3][lane] = dy;       // :64-65
-                term[4][lane] = o.z; term[5][lane] = o.w;     // :68-69
-            }
-            const uint32_t kept = __ballot_sync(0xffffffffu, keep);
-            const uint32_t add = kept & ~__ballot_sync(0xffffffffu, self);
-            nvec += (uint32_t)__popc(kept);
-            count += __popc(add);                          // :56
-            __syncwarp();
-            if (lane < 6) {
-                uint32_t m = add;
-                while (m) {                                // candidates in order, one rounded addition each
-                    const int e = __ffs(m) - 1;
-                    m &= m - 1;
-                    acc_l = __fadd_rn(acc_l, term[lane][e]);
-                }
-            }
-            __syncwarp();
-        }
-    }
-    Acc acc;
-    acc.xa = __shfl_sync(0xffffffffu, acc_l, 0); acc.ya = __shfl_sync(0xffffffffu, acc_l, 1);
-    acc.xc = __shfl_sync(0xffffffffu, acc_l, 2); acc.yc = __shfl_sync(0xffffffffu, acc_l, 3);
-    acc.xs = __shfl_sync(0xffffffffu, acc_l, 4); acc.ys = __shfl_sync(0xffffffffu, acc_l, 5);
-    acc.nvec = nvec; acc.count = count;
-    if (lane == 0) finish_bird<MATH, false, 0>(g, p, s, a, me, my_id, w, acc, d_ok, Rd, i);
-}
-
-constexpr uint32_t COLS_STEP_MAX = 4000000;   // birds: up to here the column-aligned grid pays (fewer waves: a slow CTA in the last wave is a visible tail)
+constexpr uint32_t COLS_STEP_MAX = 12000000;   // birds: up to here the column-aligned grid pays (8 M birds on a square field: 587 vs 607 us per tick;
+                                               // 16 M birds on 672 x 5376 cells: 1.131 ms either way, long columns have few straddling CTAs)
+constexpr uint32_t GENWARP_MAX = 8000;     // general birds (seam rows + seam columns) of a column-aligned launch: up to here a warp each, a thread
+                                           // each beyond (B200: 250 000 birds 41.0 vs 51.2 us per tick, 500 000 birds 64.4 vs 60.8)
 constexpr uint32_t WARP_STEP_MAX = 12288;   // birds: up to here a warp per bird beats a thread per bird (B200: crossover ~15 000)
+
+uint32_t step_warp_max() {
+    static const uint32_t v = [] { const char *e = getenv("FLK_STEP_WARP"); return e ? (uint32_t)atoi(e) : WARP_STEP_MAX; }();   // A/B runs
+    return v;
+}
 
 void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs &a, uint32_t n_upper,
                  cudaStream_t st) {
     if (n_upper == 0) return;
-    static const uint32_t warp_max = [] { const char *e = getenv("FLK_STEP_WARP"); return e ? (uint32_t)atoi(e) : WARP_STEP_MAX; }();   // A/B runs
+    const uint32_t warp_max = step_warp_max();
     if (n_upper <= warp_max && g.mode != 2 && (2 * p.k + 1) * (2 * p.k + 1) <= WARP_RUNS) {
         const dim3 blk(128), grd((n_upper + 3) / 4);
         if (p.relax) {
@@ -626,7 +673,13 @@ void launch_step(const Geom &g, const Params &p, const Store &s, const StepArgs 
     // single-GPU handles of moderate size: column-aligned grid + seam CTAs (whole-field launches only)
     if (g.mode == 0 && tile && fastg && n_upper <= colgrid_max && s.colchunk && a.cell_lo == 0 && a.math_mode == 0) {
         StepArgs ac = a;
-        ac.nseam = (3u * (uint32_t)(g.mx - 2) + bs / 32 - 1) / (bs / 32);
+        // head of the grid: a warp per general bird (three columns + three rows of the field), sized for a uniform field
+        // with a margin; the warps stride over whatever the population really is
+        static const double genwarp_max = [] { const char *e = getenv("FLK_STEP_GENWARP"); return e ? atof(e) : (double)GENWARP_MAX; }();   // A/B runs
+        const double gen = (double)n_upper * (3.0 / (double)g.ncols + 3.0 / (double)g.dh);
+        ac.gen_threads = gen > genwarp_max ? 1 : 0;
+        const double per_cta = ac.gen_threads ? (double)bs : (double)(bs / 32);
+        ac.nseam = (uint32_t)fmin(fmax(gen * 1.25 / per_cta + 8.0, 16.0), 32768.0);
         const dim3 gridc(ac.nseam + (n_upper + bs - 1) / bs + (uint32_t)g.ncols);   // every column ends with one partial chunk at most
         k_step<true, 0, true, true, false, true><<<gridc, block, 0, st>>>(g, p, s, ac);
         return;
@@ -987,24 +1040,33 @@ void launch_scatter(const Store &s, uint32_t n, int dist, cudaStream_t st) {
     k_scatter4<<<nb, 256, 0, st>>>(s, n, 0, nb);
 }
 
-// colchunk[c] = k_step CTAs needed by the columns before c (column-aligned launches); one CTA, after cell_start is final
+// Tables of the column-aligned k_step launches (single-GPU handles; one CTA, after cell_start is final).  A TILE column is
+// one whose 3x3 windows never touch the x seam: 1 .. mx-2 (ncols = mx + 1 with the slack column).
+//   colchunk[c]              k_step CTAs (chunks of FLK_STEP_BS birds) needed by the tile columns before c; [ncols] = all
+//   colchunk[ncols + 1 + c]  birds in the seam rows (0, my-1 and the slack row my) of the tile columns before c; [.. + ncols] = all
 template <int THREADS = 256>
 __device__ __forceinline__ void build_colchunk(const Store &s, uint32_t ncols, uint32_t dh) {
-    __shared__ uint32_t sh_carry;
-    if (threadIdx.x == 0) sh_carry = 0;
+    __shared__ uint32_t sh_carry[2];
+    if (threadIdx.x == 0) { sh_carry[0] = 0; sh_carry[1] = 0; }
     __syncthreads();
+    uint32_t *colseam = s.colchunk + ncols + 1;
     for (uint32_t c0 = 0; c0 < ncols; c0 += blockDim.x) {
         const uint32_t c = c0 + threadIdx.x;
-        uint32_t ch = 0;
-        if (c < ncols) ch = (s.cell_start[(c + 1) * dh] - s.cell_start[c * dh] + FLK_STEP_BS - 1) / FLK_STEP_BS;
-        uint32_t total;
+        uint32_t ch = 0, sm = 0;
+        if (c >= 1 && c + 2 < ncols) {   // tile column
+            const uint32_t *cs = s.cell_start + (size_t)c * dh;
+            ch = (cs[dh] - cs[0] + FLK_STEP_BS - 1) / FLK_STEP_BS;
+            sm = (cs[1] - cs[0]) + (cs[dh] - cs[dh - 2]);
+        }
+        uint32_t total, total2;
         const uint32_t ex = block_exclusive_scan<THREADS>(ch, &total);
-        if (c < ncols) s.colchunk[c] = sh_carry + ex;
+        const uint32_t ex2 = block_exclusive_scan<THREADS>(sm, &total2);
+        if (c < ncols) { s.colchunk[c] = sh_carry[0] + ex; colseam[c] = sh_carry[1] + ex2; }
         __syncthreads();
-        if (threadIdx.x == 0) sh_carry += total;
+        if (threadIdx.x == 0) { sh_carry[0] += total; sh_carry[1] += total2; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) s.colchunk[ncols] = sh_carry;
+    if (threadIdx.x == 0) { s.colchunk[ncols] = sh_carry[0]; colseam[ncols] = sh_carry[1]; }
 }
 
 // two staged entries per thread: both record gathers and both cell-range loads are in flight before either member
@@ -1117,7 +1179,9 @@ __global__ void __launch_bounds__(1024) k_rebin_small(const Store s, uint32_t nc
 
 void launch_rebin_small(const Store &s, uint32_t ncell, uint32_t n_write, int bump_step, cudaStream_t st, uint32_t ncols,
                         uint32_t dh) {
-    if (!s.colchunk) ncols = 0;
+    // the column tables are only read by k_step's column-aligned launches, which a population this small never gets
+    // (k_step_warp takes it)
+    if (!s.colchunk || n_write <= step_warp_max()) ncols = 0;
     k_rebin_small<<<1, 1024, 0, st>>>(s, ncell, n_write, bump_step, ncols, dh);
 }
 

@@ -50,8 +50,9 @@ struct Store {
     uint32_t *sw_spill_cnt;
     uint32_t sw_spill_cap;
     uint32_t *sw_totals;   // [2] of the last k_compact: largest cell, spilled arrivals
-    // single-GPU handles: colchunk[c] = number of k_step CTAs (chunks of FLK_STEP_BS birds) that the columns before c need,
-    // colchunk[ncols] = all of them (written with cell_start by lazy_update: k_rank / k_compact); null = not maintained
+    // single-GPU handles: colchunk[c] = number of k_step CTAs (chunks of FLK_STEP_BS birds) that the tile columns before c
+    // need, colchunk[ncols] = all of them; colchunk[ncols + 1 + c] = seam-row birds of the tile columns before c (written with
+    // cell_start by lazy_update: k_rank / k_compact / k_rebin_small); null = not maintained
     uint32_t *colchunk;
 };
 
@@ -82,7 +83,8 @@ struct StepArgs {
     int math_mode;              // 0 exact, 1 fast
     int identity;               // 1 = re-stage every owned bird unchanged (dist commit: builds the first halo)
     int skip_bands;             // tiles: the two owned rows next to each row boundary are stepped by k_step_bands, skip them
-    uint32_t nseam;             // column-aligned launches (COLS): CTAs at the head of the grid that step the seam-row cells
+    uint32_t nseam;             // column-aligned launches (COLS): CTAs at the head of the grid that step the general-path birds
+    int gen_threads;            // COLS: those CTAs use a thread per bird (large fields) instead of a warp per bird
 };
 
 void launch_ingest(const Geom &g, const Store &s, uint32_t n, const uint32_t *id, const float2 *loc,
@@ -110,6 +112,7 @@ void launch_rank(const Store &s, uint32_t n_upper, uint32_t ncell, int bump_step
 // slot-staged WRITE buffer -> READ buffer in (cell, ascending id) order, given cell_start (one pass, 8 lanes per cell)
 // the whole rebin of a small single-GPU field (classic WRITE buffer) in one launch
 constexpr uint32_t SMALL_REBIN_MAX = 4096;   // birds: up to here one CTA beats the five-launch rebin
+uint32_t step_warp_max();   // populations up to this many birds are stepped by k_step_warp
 void launch_rebin_small(const Store &s, uint32_t ncell, uint32_t n_write, int bump_step, cudaStream_t st, uint32_t ncols,
                         uint32_t dh);
 void launch_compact(const Store &s, uint32_t ncell, int bump_step, cudaStream_t st, uint32_t ncols = 0, uint32_t dh = 0);
