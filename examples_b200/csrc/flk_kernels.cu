@@ -642,7 +642,8 @@ constexpr uint32_t COLS_STEP_MAX = 12000000;   // birds: up to here the column-a
                                                // 16 M birds on 672 x 5376 cells: 1.131 ms either way, long columns have few straddling CTAs)
 constexpr uint32_t GENWARP_MAX = 8000;     // general birds (seam rows + seam columns) of a column-aligned launch: up to here a warp each, a thread
                                            // each beyond (B200: 250 000 birds 41.0 vs 51.2 us per tick, 500 000 birds 64.4 vs 60.8)
-constexpr uint32_t WARP_STEP_MAX = 12288;   // birds: up to here a warp per bird beats a thread per bird (B200: crossover ~15 000)
+constexpr uint32_t WARP_STEP_MAX = 5000;    // birds: up to here a warp per bird beats the column-aligned grid (B200: 4000 birds 22.1 vs 23.5 us per tick,
+                                            // 6000 birds 24.8 vs 22.7, 12 000 birds 34.8 vs 24.6)
 
 uint32_t step_warp_max() {
     static const uint32_t v = [] { const char *e = getenv("FLK_STEP_WARP"); return e ? (uint32_t)atoi(e) : WARP_STEP_MAX; }();   // A/B runs
